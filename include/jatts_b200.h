@@ -1,0 +1,137 @@
+/* jatts_b200 -- C ABI of the B200-native JATTS batched-synthesis path.
+ *
+ * This is the drop-in boundary for the reference's two hot-path calls:
+ *
+ *   jatts/models/fastspeech2.py:655-735   FastSpeech2.inference(text, spembs=..., alpha=...)
+ *   jatts/vocoder/vocoder.py:56-67        Vocoder.decode(c)  (-> parallel_wavegan HiFiGANGenerator.inference)
+ *
+ * as they are called from jatts/bin/tts_decode.py:230,249 and jatts/trainers/fastspeech2.py:183,205.
+ * The reference is pure Python; the host side that mirrors its classes lives in jatts_b200/*.py and binds
+ * these symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (PyTorch); h_* is a HOST pointer.
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered.  The only host
+ *     synchronisation is inside jatts_fs2_plan (the per-utterance frame counts must reach the host so
+ *     the caller can size its outputs) -- the same point where the reference synchronises
+ *     (length_regulator.py:86, repeat_interleave).
+ *   - return value: 0 on success, a negative JATTS_E_* code otherwise; jatts_last_error() returns the
+ *     message of the last failure on the calling thread.  There is no CPU fallback of any kind.
+ *   - a handle is bound to the CUDA device that was current at create time and is not re-entrant.
+ */
+#ifndef JATTS_B200_H_
+#define JATTS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JATTS_B200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define JATTS_API __attribute__((visibility("default")))
+#else
+#define JATTS_API
+#endif
+
+enum {
+  JATTS_OK = 0,
+  JATTS_E_UNSUPPORTED = -1, /* configuration outside what the kernels implement */
+  JATTS_E_INVALID = -2,     /* bad argument / shape */
+  JATTS_E_CUDA = -3,        /* CUDA runtime or driver failure (message has the code) */
+  JATTS_E_STATE = -4        /* call order violated (run before plan, ...) */
+};
+
+enum { JATTS_F32 = 0, JATTS_BF16 = 1, JATTS_I64 = 2, JATTS_I32 = 3 };
+
+/* a named, already-repacked weight tensor in device memory (the Python host side does the repacking:
+ * BatchNorm folding, tap-major layout, bf16 hi/lo split, channel padding) */
+typedef struct {
+  const char* name;
+  const void* d_ptr;
+  int64_t numel;
+  int32_t dtype;
+} jatts_tensor;
+
+typedef struct jatts_fs2 jatts_fs2;         /* FastSpeech2 text2mel engine */
+typedef struct jatts_hifigan jatts_hifigan; /* HiFi-GAN V1 generator engine */
+
+JATTS_API int jatts_abi_version(void);
+JATTS_API const char* jatts_last_error(void);
+/* number of kernels this library has launched since load (all handles); bench.py reports the delta */
+JATTS_API int64_t jatts_launch_count(void);
+
+/* ---- FastSpeech2 (replaces jatts/models/fastspeech2.py:566-735 on the inference path) ------------ */
+typedef struct {
+  int32_t idim, odim, adim, aheads;
+  int32_t elayers, eunits, dlayers, dunits;
+  int32_t ffn_kernel;                       /* positionwise_conv_kernel_size */
+  int32_t enc_cnn_kernel, dec_cnn_kernel;   /* conformer_{enc,dec}_kernel_size */
+  int32_t dur_layers, dur_chans, dur_kernel;
+  int32_t pitch_layers, pitch_chans, pitch_kernel;
+  int32_t energy_layers, energy_chans, energy_kernel;
+  int32_t postnet_layers, postnet_chans, postnet_filts;
+  int32_t spk_embed_dim;                    /* 0 = no speaker conditioning ("add" integration otherwise) */
+  int32_t max_len;                          /* rows of the precomputed linear_pos(pe) tables (<= 5000) */
+} jatts_fs2_config;
+
+JATTS_API int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor* weights, int32_t n_weights,
+                     jatts_fs2** out);
+JATTS_API void jatts_fs2_destroy(jatts_fs2* h);
+
+/* Phase 1: encoder + variance adaptor + durations.  d_tokens: int64 [sum(h_text_lens)], utterances
+ * back to back.  d_spembs: fp32 [n_utt, spk_embed_dim] or NULL.  Writes the number of mel frames of
+ * every utterance to h_n_frames[n_utt] (host) and returns after the stream has drained. */
+JATTS_API int jatts_fs2_plan(jatts_fs2* h, const int64_t* d_tokens, const int32_t* h_text_lens, int32_t n_utt,
+                   const float* d_spembs, float alpha, int32_t* h_n_frames, void* stream);
+/* Phase 2: LengthRegulator + decoder + postnet for the batch planned last.  Outputs, utterances back
+ * to back: d_mel fp32 [sum frames, odim]; d_durations int64 [sum text]; d_pitch, d_energy fp32
+ * [sum text]; d_lr_index int32 [sum frames] (token index each frame was expanded from; may be NULL). */
+JATTS_API int jatts_fs2_run(jatts_fs2* h, float* d_mel, int64_t* d_durations, float* d_pitch, float* d_energy,
+                  int32_t* d_lr_index, void* stream);
+
+/* ---- HiFi-GAN generator (replaces parallel_wavegan HiFiGANGenerator.inference behind vocoder.py:64) */
+typedef struct {
+  int32_t in_channels, out_channels, channels, kernel_size;
+  int32_t n_upsamples;
+  int32_t upsample_scales[8];
+  int32_t n_resblocks;                      /* residual blocks per stage (3) */
+  int32_t resblock_kernels[8];
+  int32_t n_dilations;                      /* dilations per residual block (3) */
+  int32_t resblock_dilations[8][8];
+  float lrelu_slope;                        /* 0.1 */
+} jatts_hifigan_config;
+
+JATTS_API int jatts_hifigan_create(const jatts_hifigan_config* cfg, const jatts_tensor* weights, int32_t n_weights,
+                         jatts_hifigan** out);
+JATTS_API void jatts_hifigan_destroy(jatts_hifigan* h);
+/* d_mel: fp32 [sum(h_mel_lens), in_channels] utterances back to back, in the caller's normalisation;
+ * the per-bin affine  c*scale + shift  of vocoder.py:57-61 is applied on load (weights "mel_scale",
+ * "mel_shift").  d_wave: fp32 [sum(h_mel_lens) * hop]. */
+JATTS_API int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int32_t* h_mel_lens, int32_t n_utt,
+                      float* d_wave, void* stream);
+
+/* ---- op-level entry points used by the parity tests (tests/test_ops_gpu.py) ------------------------ */
+typedef struct {
+  const void* d_a_hi; const void* d_a_lo;     /* bf16 [a_rows, a_ld]; a_lo NULL = single bf16 */
+  int32_t a_rows, a_ld, a_cols;                 /* a_cols: real channels (<= k_pad), 0 = k_pad */
+  const void* d_w_hi; const void* d_w_lo;     /* bf16 [taps*n_pad, k_pad] */
+  int32_t taps, n_pad, k_pad, tap_off0, tap_stride;
+  int32_t n, m_rows, block_n;
+  const uint8_t* d_frame_mask; int32_t rate, out_rows;
+  int32_t up_s, up_p, up_cout;
+  const float* d_bias; int32_t act; float slope, scale;
+  const float* d_res_f32; const void* d_res_bf16; int32_t res_ld;
+  const float* d_accum_in; float post_scale;
+  float* d_out_f32; int32_t out_f32_ld;
+  void* d_out_hi; void* d_out_lo; int32_t out_bf_ld;
+  void* d_out_act; float out_act_slope; int32_t out_act_ld;
+} jatts_conv_gemm_args;
+/* impl 0 = tcgen05 kernel (the product kernel), 1 = CUDA-core twin (test-only cross-check) */
+JATTS_API int jatts_op_conv_gemm(const jatts_conv_gemm_args* a, int32_t impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JATTS_B200_H_ */

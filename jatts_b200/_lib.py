@@ -1,0 +1,128 @@
+"""ctypes binding of include/jatts_b200.h (the C-ABI drop-in boundary).
+
+There is NO fallback: if the shared library has not been built (``python -c "import __graft_entry__ as
+g; g.build()"`` or ``make -C jatts_b200/csrc``) importing this module raises, and every call that
+returns a negative JATTS_E_* code raises ``RuntimeError`` / ``ValueError`` with the library's message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libjatts_b200.so")
+
+JATTS_F32, JATTS_BF16, JATTS_I64, JATTS_I32 = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_GLU = 0, 1, 2, 3, 4
+
+
+class Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("d_ptr", C.c_void_p), ("numel", C.c_int64), ("dtype", C.c_int32)]
+
+
+class Fs2Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "idim", "odim", "adim", "aheads", "elayers", "eunits", "dlayers", "dunits", "ffn_kernel",
+        "enc_cnn_kernel", "dec_cnn_kernel", "dur_layers", "dur_chans", "dur_kernel",
+        "pitch_layers", "pitch_chans", "pitch_kernel", "energy_layers", "energy_chans", "energy_kernel",
+        "postnet_layers", "postnet_chans", "postnet_filts", "spk_embed_dim", "max_len")]
+
+
+class HifiganConfig(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("channels", C.c_int32),
+                ("kernel_size", C.c_int32), ("n_upsamples", C.c_int32), ("upsample_scales", C.c_int32 * 8),
+                ("n_resblocks", C.c_int32), ("resblock_kernels", C.c_int32 * 8), ("n_dilations", C.c_int32),
+                ("resblock_dilations", (C.c_int32 * 8) * 8), ("lrelu_slope", C.c_float)]
+
+
+class ConvGemmArgs(C.Structure):
+    _fields_ = [
+        ("d_a_hi", C.c_void_p), ("d_a_lo", C.c_void_p), ("a_rows", C.c_int32), ("a_ld", C.c_int32),
+        ("a_cols", C.c_int32),
+        ("d_w_hi", C.c_void_p), ("d_w_lo", C.c_void_p),
+        ("taps", C.c_int32), ("n_pad", C.c_int32), ("k_pad", C.c_int32), ("tap_off0", C.c_int32),
+        ("tap_stride", C.c_int32), ("n", C.c_int32), ("m_rows", C.c_int32), ("block_n", C.c_int32),
+        ("d_frame_mask", C.c_void_p), ("rate", C.c_int32), ("out_rows", C.c_int32),
+        ("up_s", C.c_int32), ("up_p", C.c_int32), ("up_cout", C.c_int32),
+        ("d_bias", C.c_void_p), ("act", C.c_int32), ("slope", C.c_float), ("scale", C.c_float),
+        ("d_res_f32", C.c_void_p), ("d_res_bf16", C.c_void_p), ("res_ld", C.c_int32),
+        ("d_accum_in", C.c_void_p), ("post_scale", C.c_float),
+        ("d_out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
+        ("d_out_hi", C.c_void_p), ("d_out_lo", C.c_void_p), ("out_bf_ld", C.c_int32),
+        ("d_out_act", C.c_void_p), ("out_act_slope", C.c_float), ("out_act_ld", C.c_int32),
+    ]
+
+
+#: every symbol include/jatts_b200.h declares (tests/test_cabi.py checks the library exports them all)
+EXPORTS = (
+    "jatts_abi_version", "jatts_last_error", "jatts_launch_count",
+    "jatts_fs2_create", "jatts_fs2_destroy", "jatts_fs2_plan", "jatts_fs2_run",
+    "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_op_conv_gemm",
+)
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"jatts_b200: CUDA library not built ({LIB_PATH} missing). Build it with "
+            "`make -C jatts_b200/csrc` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.jatts_abi_version.restype = C.c_int
+    lib.jatts_last_error.restype = C.c_char_p
+    lib.jatts_launch_count.restype = C.c_int64
+    lib.jatts_fs2_create.argtypes = [C.POINTER(Fs2Config), C.POINTER(Tensor), C.c_int32, C.POINTER(C.c_void_p)]
+    lib.jatts_fs2_destroy.argtypes = [C.c_void_p]
+    lib.jatts_fs2_destroy.restype = None
+    lib.jatts_fs2_plan.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
+                                   C.c_float, C.POINTER(C.c_int32), C.c_void_p]
+    lib.jatts_fs2_run.argtypes = [C.c_void_p] * 7
+    lib.jatts_hifigan_create.argtypes = [C.POINTER(HifiganConfig), C.POINTER(Tensor), C.c_int32,
+                                         C.POINTER(C.c_void_p)]
+    lib.jatts_hifigan_destroy.argtypes = [C.c_void_p]
+    lib.jatts_hifigan_destroy.restype = None
+    lib.jatts_hifigan_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
+                                      C.c_void_p]
+    lib.jatts_op_conv_gemm.argtypes = [C.POINTER(ConvGemmArgs), C.c_int32, C.c_void_p]
+    if lib.jatts_abi_version() != 1:
+        raise RuntimeError("jatts_b200: ABI version mismatch between the Python host side and the library")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "") -> None:
+    """Map a negative JATTS_E_* return code to a Python exception (vocoder.py:22-24 style: fail loudly)."""
+    if rc == 0:
+        return
+    msg = (lib.jatts_last_error() or b"").decode(errors="replace")
+    text = f"jatts_b200 {what} failed (code {rc}): {msg}"
+    if rc == -2:
+        raise ValueError(text)
+    if rc == -1:
+        raise NotImplementedError(text)
+    raise RuntimeError(text)
+
+
+_DT = None
+
+
+def tensor_table(named):
+    """dict name -> torch tensor (device, contiguous)  ->  (ctypes array, keep-alive list)."""
+    import torch
+
+    global _DT
+    if _DT is None:
+        _DT = {torch.float32: JATTS_F32, torch.bfloat16: JATTS_BF16, torch.int64: JATTS_I64, torch.int32: JATTS_I32}
+    arr = (Tensor * len(named))()
+    keep = []
+    for i, (k, t) in enumerate(named.items()):
+        assert t.is_contiguous() and t.is_cuda, k
+        kb = k.encode()
+        keep.append((kb, t))
+        arr[i] = Tensor(kb, t.data_ptr(), t.numel(), _DT[t.dtype])
+    return arr, keep
+
+
+def launch_count() -> int:
+    return int(lib.jatts_launch_count())

@@ -1,0 +1,179 @@
+"""Weight repacking for the CUDA engines (host side, done once at load).
+
+Reference-format tensors -> the layouts the kernels consume: tap-major [taps][N_pad][K_pad] bf16
+(hi/lo split pairs for the fp32-faithful text2mel GEMMs), BatchNorm folded into the preceding
+convolution, GLU halves interleaved per 128-wide tile, ConvTranspose1d split into its two polyphase
+taps, relative-position tables pre-multiplied by ``linear_pos``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+BN_EPS = 1e-5
+PE_MAX_LEN = 5000  # jatts/modules/positional_encoding.py:212 (initial max_len of the legacy table)
+
+
+def round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def pick_block_n(n_cols: int, split: bool) -> int:
+    """mirror of csrc/engine_common.cuh::pick_block_n"""
+    if split:
+        return 128
+    for b in (256, 128, 64):
+        if n_cols % b == 0:
+            return b
+    return 32
+
+
+def split_bf16(w: torch.Tensor):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def pack_taps(w_tnk: torch.Tensor, split: bool, out: dict, name: str, bias=None):
+    """w_tnk: fp32 [taps, N, K] -> name.hi (/.lo) as [taps, N_pad, K_pad] bf16 (+ name.b)."""
+    taps, n, k = w_tnk.shape
+    bn = pick_block_n(n, split)
+    n_pad, k_pad = round_up(n, bn), round_up(k, 64)
+    buf = torch.zeros(taps, n_pad, k_pad, dtype=torch.float32)
+    buf[:, :n, :k] = w_tnk
+    if split:
+        hi, lo = split_bf16(buf)
+        out[name + ".hi"], out[name + ".lo"] = hi.contiguous(), lo.contiguous()
+    else:
+        out[name + ".hi"] = buf.to(torch.bfloat16).contiguous()
+    if bias is not None:
+        out[name + ".b"] = bias.float().contiguous()
+
+
+def conv1d_taps(weight: torch.Tensor) -> torch.Tensor:
+    """torch Conv1d weight [C_out, C_in, k] (or Linear [C_out, C_in]) -> [k, C_out, C_in]."""
+    if weight.dim() == 2:
+        weight = weight.unsqueeze(-1)
+    return weight.permute(2, 0, 1).contiguous().float()
+
+
+def glu_interleave(w_nk: torch.Tensor, bias: torch.Tensor, block_n: int = 128):
+    """pointwise_conv1 rows [a(0..D) | gate(D..2D)] -> per 128-wide tile [64 a | 64 gate]
+    (F.glu(dim=1): first half * sigmoid(second half), convolution.py:71)."""
+    d = w_nk.shape[0] // 2
+    half = block_n // 2
+    assert d % half == 0
+    idx = []
+    for t in range(d // half):
+        idx += list(range(t * half, (t + 1) * half))
+        idx += list(range(d + t * half, d + (t + 1) * half))
+    idx = torch.tensor(idx)
+    return w_nk[idx], bias[idx]
+
+
+def legacy_pe_table(d_model: int, length: int) -> torch.Tensor:
+    """positional_encoding.py:36-57 with reverse=True at max_len 5000: row n = sinusoid(4999 - n)."""
+    position = torch.arange(PE_MAX_LEN - 1, -1, -1.0, dtype=torch.float32).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / d_model))
+    pe = torch.zeros(PE_MAX_LEN, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe[:length]
+
+
+def pack_fs2(sd: dict, cfg: dict, max_len: int) -> dict:
+    """reference FastSpeech2 state_dict (CPU fp32) -> engine weight table (CPU tensors)."""
+    out: dict = {}
+    d = cfg["adim"]
+    pe = legacy_pe_table(d, max_len).double()
+
+    def ln(dst, src):
+        out[dst + ".g"] = sd[src + ".weight"].float().contiguous()
+        out[dst + ".b"] = sd[src + ".bias"].float().contiguous()
+
+    def conformer(dst, src, n_layers):
+        for i in range(n_layers):
+            p, q = f"{dst}.{i}.", f"{src}.encoders.{i}."
+            for a, b in (("ln_ffm", "norm_ff_macaron"), ("ln_mha", "norm_mha"), ("ln_conv", "norm_conv"),
+                         ("ln_ff", "norm_ff"), ("ln_final", "norm_final")):
+                ln(p + a, q + b)
+            for a, b in (("ffm", "feed_forward_macaron"), ("ff", "feed_forward")):
+                pack_taps(conv1d_taps(sd[q + b + ".w_1.weight"]), True, out, p + a + "_w1", sd[q + b + ".w_1.bias"])
+                pack_taps(conv1d_taps(sd[q + b + ".w_2.weight"]), True, out, p + a + "_w2", sd[q + b + ".w_2.bias"])
+            sa = q + "self_attn."
+            wqkv = torch.cat([sd[sa + f"linear_{n}.weight"] for n in "qkv"], 0)
+            bqkv = torch.cat([sd[sa + f"linear_{n}.bias"] for n in "qkv"], 0)
+            pack_taps(conv1d_taps(wqkv), True, out, p + "qkv", bqkv)
+            pack_taps(conv1d_taps(sd[sa + "linear_out.weight"]), True, out, p + "out", sd[sa + "linear_out.bias"])
+            # p = linear_pos(pos_emb) is batch independent (attention.py:182-184): precompute per layer
+            out[p + "pos"] = (pe @ sd[sa + "linear_pos.weight"].double().t()).float().contiguous()
+            out[p + "bias_u"] = sd[sa + "pos_bias_u"].float().reshape(-1).contiguous()
+            out[p + "bias_v"] = sd[sa + "pos_bias_v"].float().reshape(-1).contiguous()
+            cm = q + "conv_module."
+            w1, b1 = glu_interleave(sd[cm + "pointwise_conv1.weight"][:, :, 0].float(), sd[cm + "pointwise_conv1.bias"].float())
+            pack_taps(w1.unsqueeze(0), True, out, p + "pw1", b1)
+            # depthwise conv + eval BatchNorm folded: y = (conv(x)+b - mean) * g/sqrt(var+eps) + beta
+            scale = sd[cm + "norm.weight"].double() / torch.sqrt(sd[cm + "norm.running_var"].double() + BN_EPS)
+            wdw = sd[cm + "depthwise_conv.weight"][:, 0, :].double() * scale[:, None]          # [D, k]
+            bdw = (sd[cm + "depthwise_conv.bias"].double() - sd[cm + "norm.running_mean"].double()) * scale \
+                + sd[cm + "norm.bias"].double()
+            out[p + "dw.wT"] = wdw.t().float().contiguous()                                       # [k, D]
+            out[p + "dw.b"] = bdw.float().contiguous()
+            pack_taps(conv1d_taps(sd[cm + "pointwise_conv2.weight"]), True, out, p + "pw2", sd[cm + "pointwise_conv2.bias"])
+        ln(dst + ".after_norm", src + ".after_norm")
+
+    conformer("enc", "encoder", cfg["elayers"])
+    conformer("dec", "decoder", cfg["dlayers"])
+
+    def predictor(dst, src, n_layers):
+        for i in range(n_layers):
+            pack_taps(conv1d_taps(sd[f"{src}.conv.{i}.0.weight"]), True, out, f"{dst}.conv{i}", sd[f"{src}.conv.{i}.0.bias"])
+            ln(f"{dst}.ln{i}", f"{src}.conv.{i}.2")
+        out[dst + ".lin_w"] = sd[src + ".linear.weight"].float().reshape(-1).contiguous()
+        out[dst + ".lin_b"] = sd[src + ".linear.bias"].float().reshape(1).contiguous()
+
+    predictor("dur", "duration_predictor", cfg["duration_predictor_layers"])
+    predictor("pitch", "pitch_predictor", cfg["pitch_predictor_layers"])
+    predictor("energy", "energy_predictor", cfg["energy_predictor_layers"])
+    out["emb"] = sd["encoder.embed.0.weight"].float().contiguous()
+    for n in ("pitch", "energy"):
+        out[n + "_embed.w"] = sd[n + "_embed.0.weight"][:, 0, 0].float().contiguous()
+        out[n + "_embed.b"] = sd[n + "_embed.0.bias"].float().contiguous()
+    if cfg.get("spk_embed_dim"):
+        out["spk.w"] = sd["projection.weight"].float().contiguous()
+        out["spk.b"] = sd["projection.bias"].float().contiguous()
+    pack_taps(conv1d_taps(sd["feat_out.weight"]), True, out, "feat_out", sd["feat_out.bias"])
+    for i in range(cfg["postnet_layers"]):
+        q = f"postnet.postnet.{i}."
+        w = sd[q + "0.weight"].double()
+        scale = sd[q + "1.weight"].double() / torch.sqrt(sd[q + "1.running_var"].double() + BN_EPS)
+        wf = (w * scale[:, None, None]).float()
+        bf = (sd[q + "1.bias"].double() - sd[q + "1.running_mean"].double() * scale).float()
+        pack_taps(conv1d_taps(wf), True, out, f"postnet{i}", bf)
+    return out
+
+
+def pack_hifigan(sd: dict, cfg: dict, mel_scale: torch.Tensor, mel_shift: torch.Tensor) -> dict:
+    """parallel_wavegan HiFiGANGenerator state_dict (weight norm already folded) -> engine table."""
+    out: dict = {}
+    pack_taps(conv1d_taps(sd["input_conv.weight"]), False, out, "input_conv", sd["input_conv.bias"])
+    nb = len(cfg["resblock_kernel_sizes"])
+    for i, s in enumerate(cfg["upsample_scales"]):
+        w = sd[f"upsamples.{i}.1.weight"].float()  # ConvTranspose1d: [C_in, C_out, 2s]
+        ci, co, k = w.shape
+        assert k == 2 * s
+        # out[t] = x[j] w[:,:,q] + x[j-1] w[:,:,q+s],  j=(t+p)//s, q=(t+p)%s  
+        tap0 = w[:, :, :s].permute(2, 1, 0).reshape(s * co, ci)
+        tap1 = w[:, :, s:].permute(2, 1, 0).reshape(s * co, ci)
+        pack_taps(torch.stack([tap0, tap1], 0), False, out, f"ups{i}", sd[f"upsamples.{i}.1.bias"])
+        for j in range(nb):
+            for d in range(len(cfg["resblock_dilations"][j])):
+                b = f"blocks.{i * nb + j}."
+                pack_taps(conv1d_taps(sd[b + f"convs1.{d}.1.weight"]), False, out, f"rb{i}_{j}.c1_{d}", sd[b + f"convs1.{d}.1.bias"])
+                pack_taps(conv1d_taps(sd[b + f"convs2.{d}.1.weight"]), False, out, f"rb{i}_{j}.c2_{d}", sd[b + f"convs2.{d}.1.bias"])
+    out["output.w"] = sd["output_conv.1.weight"][0].t().float().contiguous()  # [k, C]
+    out["output.b"] = sd["output_conv.1.bias"].float().reshape(1).contiguous()
+    out["mel_scale"] = mel_scale.float().contiguous()
+    out["mel_shift"] = mel_shift.float().contiguous()
+    return out

@@ -1,0 +1,31 @@
+// C-ABI glue: version / error / launch counter and the op-level test entry point.
+#include "engine_common.cuh"
+
+using namespace jb;
+
+extern "C" int jatts_abi_version(void) { return JATTS_B200_ABI_VERSION; }
+extern "C" const char* jatts_last_error(void) { return get_last_error(); }
+extern "C" int64_t jatts_launch_count(void) { return g_launch_count; }
+
+extern "C" int jatts_op_conv_gemm(const jatts_conv_gemm_args* a, int32_t impl, void* stream) {
+  JB_REQUIRE(a != nullptr, JATTS_E_INVALID, "op_conv_gemm: null args");
+  ConvGemmProblem p{};
+  p.a_hi = static_cast<const bf16*>(a->d_a_hi);
+  p.a_lo = static_cast<const bf16*>(a->d_a_lo);
+  p.a_rows = a->a_rows; p.a_ld = a->a_ld; p.a_cols = a->a_cols;
+  p.w_hi = static_cast<const bf16*>(a->d_w_hi);
+  p.w_lo = static_cast<const bf16*>(a->d_w_lo);
+  p.taps = a->taps; p.n_pad = a->n_pad; p.k_pad = a->k_pad; p.tap_off0 = a->tap_off0; p.tap_stride = a->tap_stride;
+  p.n = a->n; p.m_rows = a->m_rows; p.block_n = a->block_n;
+  p.frame_mask = a->d_frame_mask; p.rate = a->rate; p.out_rows = a->out_rows;
+  p.up_s = a->up_s; p.up_p = a->up_p; p.up_cout = a->up_cout;
+  ConvGemmEpilogue& e = p.ep;
+  e.bias = a->d_bias; e.act = a->act; e.slope = a->slope; e.scale = a->scale;
+  e.res_f32 = a->d_res_f32; e.res_bf16 = static_cast<const bf16*>(a->d_res_bf16); e.res_ld = a->res_ld;
+  e.accum_in = a->d_accum_in; e.post_scale = a->post_scale;
+  e.out_f32 = a->d_out_f32; e.out_f32_ld = a->out_f32_ld;
+  e.out_hi = static_cast<bf16*>(a->d_out_hi); e.out_lo = static_cast<bf16*>(a->d_out_lo); e.out_bf_ld = a->out_bf_ld;
+  e.out_act = static_cast<bf16*>(a->d_out_act); e.out_act_slope = a->out_act_slope; e.out_act_ld = a->out_act_ld;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return impl == 0 ? conv_gemm_tc(p, s) : conv_gemm_simt_debug(p, s);
+}

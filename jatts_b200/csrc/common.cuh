@@ -1,0 +1,101 @@
+// Shared device/host helpers for the jatts_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+namespace jb {
+
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing: every C-ABI entry returns 0 or a negative JATTS_E_* code; the message of the last
+// failure on this thread is kept for jatts_last_error().
+// ----------------------------------------------------------------------------------------------
+extern long long g_launch_count;
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+
+#define JB_CUDA_OK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      jb::set_last_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +     \
+                         __FILE__ + ":" + std::to_string(__LINE__));                              \
+      return -3; /* JATTS_E_CUDA */                                                               \
+    }                                                                                             \
+  } while (0)
+
+// after every kernel launch: count it (jatts_launch_count) and surface launch errors
+#define JB_KERNEL_OK()                                                                            \
+  do {                                                                                            \
+    ++jb::g_launch_count;                                                                         \
+    JB_CUDA_OK(cudaGetLastError());                                                               \
+  } while (0)
+
+#define JB_REQUIRE(cond, code, msg)                                                               \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      jb::set_last_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +                 \
+                         std::to_string(__LINE__));                                               \
+      return (code);                                                                              \
+    }                                                                                             \
+  } while (0)
+
+#define JB_PROPAGATE(expr)                                                                        \
+  do {                                                                                            \
+    int _rc = (expr);                                                                             \
+    if (_rc != 0) return _rc;                                                                     \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// packed-with-gaps row layout shared by every kernel
+//
+// A batch of utterances is stored as ONE [rows, C] channels-last matrix.  Utterance b owns rows
+// [seg_start[b]*rate, (seg_start[b]+seg_len[b])*rate); between utterances (and before the first /
+// after the last) there are >= GAP zero rows at rate 1, i.e. GAP*rate rows at an upsampled rate.
+// Convolutions therefore see each utterance's own zero padding with no per-tap boundary test:
+// gap rows are zero at allocation and no kernel ever writes them (stores are masked by
+// frame_mask[row / rate]).
+// ----------------------------------------------------------------------------------------------
+struct RowLayout {
+  const uint8_t* frame_mask;  // [n_frames_rows] 1 = row belongs to an utterance (rate-1 granularity)
+  const int* frame_seg;       // [n_frames_rows] utterance index or -1
+  const int* seg_start;       // [nseg] first row (rate-1 units)
+  const int* seg_len;         // [nseg] length  (rate-1 units)
+  int nseg;
+  int n_rows;                 // rows at rate 1 (including gaps)
+};
+
+static constexpr int kGapRows = 8;
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+#ifdef __CUDACC__
+// bf16 hi/lo split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|  (SURVEY.md 8(a) precision budget)
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#endif
+
+}  // namespace jb

@@ -1,0 +1,66 @@
+// Implicit-GEMM Conv1d / ConvTranspose1d / Linear on tcgen05 tensor cores (sm_100a).
+//
+//   out[row, n] = epilogue( sum_{tap j} sum_{c} A[row + tap_off0 + j*tap_stride, c] * W[j][n][c] )
+//
+// A is a channels-last activation matrix [rows, C_in_pad] in bf16 (optionally a hi/lo pair: "split"
+// mode, 3 MMAs per K step = fp32-faithful products, SURVEY.md 8(a) precision budget), W is
+// [taps][N_pad][C_in_pad] bf16 (hi/lo in split mode).  Row shifts between taps are TMA coordinates;
+// per-utterance zero padding comes from the packed-with-gaps layout (common.cuh) and from TMA
+// out-of-bounds zero fill at the ends of the buffer.
+#pragma once
+#include "common.cuh"
+
+namespace jb {
+
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3, ACT_GLU = 4 };
+
+struct ConvGemmEpilogue {
+  const float* bias;        // [N] (GLU: [N_pad] permuted like the weights) or null
+  int act;                  // ACT_*
+  float slope;              // for ACT_LRELU
+  float scale;              // v = act(acc + bias) * scale
+  const float* res_f32;     // v += res_f32[row*res_ld + n]
+  const bf16* res_bf16;     // v += res_bf16[row*res_ld + n]
+  int res_ld;
+  const float* accum_in;    // v += accum_in[row*out_f32_ld + n]   (MRF branch sum)
+  float post_scale;         // v *= post_scale
+  float* out_f32;           // optional fp32 output
+  int out_f32_ld;
+  bf16* out_hi;             // optional bf16(v)
+  bf16* out_lo;             // optional bf16(v - hi)
+  int out_bf_ld;
+  bf16* out_act;            // optional bf16(leaky_relu(v, out_act_slope))  (next conv's operand)
+  float out_act_slope;
+  int out_act_ld;
+};
+
+struct ConvGemmProblem {
+  // operands
+  const bf16* a_hi;  const bf16* a_lo;   // [a_rows, a_ld]; a_lo null => plain bf16
+  int a_rows, a_ld;
+  int a_cols;                            // real channels of A (<= k_pad; TMA zero-fills the rest); 0 => k_pad
+  const bf16* w_hi;  const bf16* w_lo;   // [taps*n_pad, k_pad]
+  int taps, n_pad, k_pad;                // k_pad = C_in padded to 64
+  int tap_off0, tap_stride;
+  int n;                                 // real output columns (GLU: real outputs = n, weights hold 2n)
+  int m_rows;                            // rows to compute (output row space before remap)
+  int block_n;                           // 32 / 64 / 128 / 256
+  // row validity (output side): rows are valid iff frame_mask[out_row / rate] != 0; null => all valid
+  const uint8_t* frame_mask;
+  int rate;                              // rows per mask entry on the OUTPUT side
+  int out_rows;                          // bound on out_row
+  // transposed-conv (polyphase) row remap: 0 => plain.  out_row = row*up_s + (n / up_cout) - up_p,
+  // out_col = n % up_cout
+  int up_s, up_p, up_cout;
+  ConvGemmEpilogue ep;
+};
+
+// Launch the tcgen05 kernel.  Returns 0 / negative JATTS_E_*.
+int conv_gemm_tc(const ConvGemmProblem& p, cudaStream_t stream);
+// Plain CUDA-core kernel with identical semantics; used ONLY by the test entry point to bisect
+// tensor-core kernel bugs from host-side packing bugs.  Never on the product path.
+int conv_gemm_simt_debug(const ConvGemmProblem& p, cudaStream_t stream);
+
+int num_sms();
+
+}  // namespace jb

@@ -1,0 +1,699 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernel for sm_100a.  See conv_gemm.cuh.
+//
+// Persistent, warp-specialised CTA (192 threads, 1 CTA per SM):
+//   warp 0      TMA producer   (one elected lane; cp.async.bulk.tensor.2d, 128B swizzle)
+//   warp 1      MMA issuer     (one elected lane; tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16)
+//               + TMEM allocation / deallocation (whole warp)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> bias/activation/residual -> global)
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue),
+// static tile scheduler (tile = blockIdx.x + i*gridDim.x, n fastest so CTAs share the A rows in L2).
+//
+// K loop = taps x (C_in_pad / 64).  Per K block the producer loads a [128 rows, 64 ch] slab of the
+// activation matrix at row coordinate m0 + tap_off0 + tap*tap_stride (negative / past-the-end rows
+// are zero-filled by TMA) and a [BLOCK_N, 64] slab of the tap's weight matrix.  In SPLIT mode each
+// operand is a bf16 hi/lo pair and every K step issues hi*hi + lo*hi + hi*lo into the same fp32
+// TMEM accumulator (lo*lo is 2^-18 relative and dropped).
+#include <mutex>
+
+#include "conv_gemm.cuh"
+
+namespace jb {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t.reg .b32 R;\n\t"
+      "elect.sync R|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trapped launch (reported as a CUDA error) instead of a hung
+// GPU.  try_wait itself blocks for a HW time slice, so the bound is generous (seconds).
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_ns() - t0 > 4000000000ull) {  // 4 s
+      printf("jatts_b200: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout_type SWIZZLE_128B=2 [61,64).)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;             // LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO = 1024 B
+  d |= static_cast<uint64_t>(1) << 46;             // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1),
+// both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int kThreads = 192;
+
+struct KernelParams {
+  int taps, k_chunks, n_pad;
+  int tap_off0, tap_stride;
+  int n;  // real output columns (GLU: outputs)
+  int m_rows;
+  int num_m_tiles, num_n_tiles;
+  const uint8_t* frame_mask;
+  int rate, out_rows;
+  int up_s, up_p, up_cout;
+  ConvGemmEpilogue ep;
+};
+
+template <int BLOCK_N, bool SPLIT>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int MAX_STAGES = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ACT_LRELU) return v > 0.0f ? v : v * slope;
+  if (act == ACT_TANH) return tanhf(v);
+  return v;
+}
+
+// Finish one row segment of NV consecutive output columns starting at column `col` of output row
+// `orow`; `v` already holds act(acc+bias)*scale (or the GLU product).
+template <int NV>
+__device__ __forceinline__ void store_row_segment(const ConvGemmEpilogue& ep, float (&v)[NV], long long orow,
+                                                  int col, int n_limit) {
+  const bool full = (col + NV <= n_limit);
+  if (ep.res_f32) {
+    const float* r = ep.res_f32 + orow * ep.res_ld + col;
+    if (full && (ep.res_ld & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(r + i);
+        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (col + i < n_limit) v[i] += r[i];
+    }
+  }
+  if (ep.res_bf16) {
+    const bf16* r = ep.res_bf16 + orow * ep.res_ld + col;
+    if (full && (ep.res_ld & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 8) {
+        uint4 t = *reinterpret_cast<const uint4*>(r + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(h[j]);
+          v[i + 2 * j] += f.x; v[i + 2 * j + 1] += f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (col + i < n_limit) v[i] += __bfloat162float(r[i]);
+    }
+  }
+  if (ep.accum_in) {
+    const float* r = ep.accum_in + orow * ep.out_f32_ld + col;
+    if (full && (ep.out_f32_ld & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(r + i);
+        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (col + i < n_limit) v[i] += r[i];
+    }
+  }
+  if (ep.post_scale != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] *= ep.post_scale;
+  }
+  if (ep.out_f32) {
+    float* o = ep.out_f32 + orow * ep.out_f32_ld + col;
+    if (full && (ep.out_f32_ld & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (col + i < n_limit) o[i] = v[i];
+    }
+  }
+  if (ep.out_hi) {
+    bf16* oh = ep.out_hi + orow * ep.out_bf_ld + col;
+    bf16* ol = ep.out_lo ? ep.out_lo + orow * ep.out_bf_ld + col : nullptr;
+    if (full && (ep.out_bf_ld & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 8) {
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = v[i + 2 * j], b = v[i + 2 * j + 1];
+          bf16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+          __nv_bfloat162 hh = __halves2bfloat162(ah, bh);
+          ph[j] = *reinterpret_cast<uint32_t*>(&hh);
+          pl[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+        }
+        *reinterpret_cast<uint4*>(oh + i) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (ol) *reinterpret_cast<uint4*>(ol + i) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (col + i < n_limit) {
+          bf16 h = __float2bfloat16_rn(v[i]);
+          oh[i] = h;
+          if (ol) ol[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+        }
+    }
+  }
+  if (ep.out_act) {
+    bf16* oa = ep.out_act + orow * ep.out_act_ld + col;
+    const float s = ep.out_act_slope;
+    if (full && (ep.out_act_ld & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 8) {
+        uint32_t pa[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = v[i + 2 * j], b = v[i + 2 * j + 1];
+          pa[j] = pack_bf16x2(a > 0.f ? a : a * s, b > 0.f ? b : b * s);
+        }
+        *reinterpret_cast<uint4*>(oa + i) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (col + i < n_limit) {
+          float a = v[i];
+          oa[i] = __float2bfloat16_rn(a > 0.f ? a : a * s);
+        }
+    }
+  }
+}
+
+template <int BLOCK_N, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const __grid_constant__ KernelParams P) {
+  using C = Cfg<BLOCK_N, SPLIT>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = P.num_m_tiles * P.num_n_tiles;
+  const int k_iters = P.taps * P.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_b_hi);
+    if (SPLIT) {
+      tma_prefetch_desc(&tm_a_lo);
+      tma_prefetch_desc(&tm_b_lo);
+    }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / P.num_n_tiles) * BLOCK_M;
+        const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+        for (int tap = 0; tap < P.taps; ++tap) {
+          const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
+          const int brow = tap * P.n_pad + n0;
+          for (int kc = 0; kc < P.k_chunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* s = smem + stage * C::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_2d(&tm_a_hi, &full_bar[stage], s, kc * BLOCK_K, arow);
+            tma_load_2d(&tm_b_hi, &full_bar[stage], s + C::A_BYTES, kc * BLOCK_K, brow);
+            if (SPLIT) {
+              tma_load_2d(&tm_a_lo, &full_bar[stage], s + C::A_BYTES + C::B_BYTES, kc * BLOCK_K, arow);
+              tma_load_2d(&tm_b_lo, &full_bar[stage], s + 2 * C::A_BYTES + C::B_BYTES, kc * BLOCK_K, brow);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t da_hi = make_sw128_desc(sa);
+          const uint64_t db_hi = make_sw128_desc(sa + C::A_BYTES);
+          const uint64_t da_lo = make_sw128_desc(sa + C::A_BYTES + C::B_BYTES);
+          const uint64_t db_lo = make_sw128_desc(sa + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
+            tc_mma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (it | k) != 0 ? 1u : 0u);
+            if (SPLIT) {
+              tc_mma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+              tc_mma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+            }
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lane_group = warp & 3;  // TMEM lanes [32*lane_group, +32) are the ones this warp may read
+    const ConvGemmEpilogue& ep = P.ep;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / P.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+      const int row = m0 + lane_group * 32 + lane;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) +
+                             static_cast<uint32_t>(acc * BLOCK_N);
+      if (ep.act == ACT_GLU) {
+        // tile columns [0, BLOCK_N/2) hold the linear half, [BLOCK_N/2, BLOCK_N) the gate half of the
+        // same BLOCK_N/2 output channels (weights are interleaved per tile on the host).
+        constexpr int HALF = BLOCK_N / 2;
+        bool valid = row < P.m_rows;
+        if (valid && P.frame_mask) valid = P.frame_mask[row / P.rate] != 0;
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 32) {
+          uint32_t ra[32], rb[32];
+          tmem_ld32(taddr + c, ra);
+          tmem_ld32(taddr + HALF + c, rb);
+          tmem_ld_wait();
+          if (valid) {
+            float v[32];
+            const int ocol = n0 / 2 + c;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float a = __uint_as_float(ra[i]) + (ep.bias ? __ldg(ep.bias + n0 + c + i) : 0.f);
+              float g = __uint_as_float(rb[i]) + (ep.bias ? __ldg(ep.bias + n0 + HALF + c + i) : 0.f);
+              v[i] = a * (1.0f / (1.0f + __expf(-g))) * ep.scale;
+            }
+            store_row_segment<32>(ep, v, row, ocol, P.n);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+          const int ncol = n0 + c;  // column in GEMM-N space
+          long long orow = row;
+          int ocol = ncol;
+          int n_limit = P.n;
+          if (P.up_s > 0) {
+            const int q = ncol / P.up_cout;
+            orow = static_cast<long long>(row) * P.up_s + q - P.up_p;
+            ocol = ncol - q * P.up_cout;
+            n_limit = (ncol < P.n) ? P.up_cout : 0;
+          }
+          bool valid = row < P.m_rows && orow >= 0 && orow < P.out_rows && ocol < n_limit;
+          if (valid && P.frame_mask) valid = P.frame_mask[orow / P.rate] != 0;
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x = __uint_as_float(r[i]);
+              if (ep.bias) x += __ldg(ep.bias + (P.up_s > 0 ? ocol + i : ncol + i < P.n ? ncol + i : 0));
+              v[i] = apply_act(x, ep.act, ep.slope) * ep.scale;
+            }
+            store_row_segment<32>(ep, v, orow, ocol, n_limit);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, ld] matrix, box = [box_rows, 64 cols], 128B swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* map, const bf16* base, long long rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  JB_REQUIRE(fn != nullptr, -3, "cuTensorMapEncodeTiled entry point not available");
+  JB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, -2, "TMA base must be 16-byte aligned");
+  JB_REQUIRE((ld * 2) % 16 == 0, -2, "TMA row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  JB_REQUIRE(r == CUDA_SUCCESS, -3, "cuTensorMapEncodeTiled failed (code " + std::to_string(static_cast<int>(r)) + ")");
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N, bool SPLIT>
+static int launch(const ConvGemmProblem& p, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, SPLIT>;
+  static_assert(C::STAGES >= 2, "need at least a double buffer");
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  const int a_cols = p.a_cols > 0 ? p.a_cols : p.k_pad;
+  JB_PROPAGATE(make_tmap(&ta_hi, p.a_hi, p.a_rows, a_cols, p.a_ld, BLOCK_M));
+  JB_PROPAGATE(make_tmap(&tb_hi, p.w_hi, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BLOCK_N));
+  if (SPLIT) {
+    JB_PROPAGATE(make_tmap(&ta_lo, p.a_lo, p.a_rows, a_cols, p.a_ld, BLOCK_M));
+    JB_PROPAGATE(make_tmap(&tb_lo, p.w_lo, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BLOCK_N));
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  KernelParams kp;
+  kp.taps = p.taps;
+  kp.k_chunks = p.k_pad / BLOCK_K;
+  kp.n_pad = p.n_pad;
+  kp.tap_off0 = p.tap_off0;
+  kp.tap_stride = p.tap_stride;
+  kp.n = p.n;
+  kp.m_rows = p.m_rows;
+  kp.num_m_tiles = ceil_div(p.m_rows, BLOCK_M);
+  kp.num_n_tiles = p.n_pad / BLOCK_N;
+  kp.frame_mask = p.frame_mask;
+  kp.rate = p.rate > 0 ? p.rate : 1;
+  kp.out_rows = p.out_rows;
+  kp.up_s = p.up_s;
+  kp.up_p = p.up_p;
+  kp.up_cout = p.up_cout > 0 ? p.up_cout : 1;
+  kp.ep = p.ep;
+  auto kern = conv_gemm_tc_kernel<BLOCK_N, SPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = kp.num_m_tiles * kp.num_n_tiles;
+  if (tiles == 0) return 0;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, kp);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+static int validate(const ConvGemmProblem& p) {
+  JB_REQUIRE(p.a_hi && p.w_hi, -2, "conv_gemm: null operand");
+  JB_REQUIRE(p.k_pad > 0 && p.k_pad % BLOCK_K == 0, -2, "conv_gemm: k_pad must be a multiple of 64");
+  JB_REQUIRE(p.a_cols >= 0 && p.a_cols <= p.k_pad && p.a_ld >= (p.a_cols > 0 ? p.a_cols : p.k_pad), -2,
+             "conv_gemm: need a_cols <= k_pad and a_ld >= a_cols");
+  JB_REQUIRE(p.block_n == 32 || p.block_n == 64 || p.block_n == 128 || p.block_n == 256, -2,
+             "conv_gemm: block_n must be 32/64/128/256");
+  JB_REQUIRE(p.n_pad > 0 && p.n_pad % p.block_n == 0, -2, "conv_gemm: n_pad must be a multiple of block_n");
+  JB_REQUIRE(p.taps >= 1, -2, "conv_gemm: taps");
+  JB_REQUIRE((p.a_lo == nullptr) == (p.w_lo == nullptr), -2, "conv_gemm: split mode needs both a_lo and w_lo");
+  if (p.ep.act == ACT_GLU) {
+    JB_REQUIRE(p.block_n >= 64 && p.up_s == 0, -2, "conv_gemm: GLU needs block_n >= 64 and no upsampling");
+    JB_REQUIRE(p.n * 2 <= p.n_pad, -2, "conv_gemm: GLU weights must hold 2n columns");
+  } else {
+    JB_REQUIRE(p.n <= p.n_pad, -2, "conv_gemm: n > n_pad");
+  }
+  if (p.up_s > 0) JB_REQUIRE(p.up_cout % 32 == 0 && p.n % p.up_cout == 0, -2, "conv_gemm: upsample needs C_out % 32 == 0");
+  JB_REQUIRE(p.ep.out_f32 || p.ep.out_hi || p.ep.out_act, -2, "conv_gemm: no output requested");
+  if (p.ep.accum_in) JB_REQUIRE(p.ep.out_f32_ld > 0, -2, "conv_gemm: accum_in uses out_f32_ld");
+  return 0;
+}
+
+int conv_gemm_tc(const ConvGemmProblem& p, cudaStream_t stream) {
+  JB_PROPAGATE(validate(p));
+  const bool split = p.a_lo != nullptr;
+  switch (p.block_n) {
+    case 32: return split ? launch<32, true>(p, stream) : launch<32, false>(p, stream);
+    case 64: return split ? launch<64, true>(p, stream) : launch<64, false>(p, stream);
+    case 128: return split ? launch<128, true>(p, stream) : launch<128, false>(p, stream);
+    case 256: return split ? launch<256, true>(p, stream) : launch<256, false>(p, stream);
+  }
+  return -2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core debug twin (test-only; see header)
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_gemm_simt_kernel(const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo, int a_rows, int a_ld,
+                                      const bf16* __restrict__ w_hi, const bf16* __restrict__ w_lo, int k_pad,
+                                      int a_cols, int block_n, KernelParams P) {
+  const int ncol = blockIdx.x * blockDim.x + threadIdx.x;  // GEMM-N column
+  const int row = blockIdx.y;
+  const bool glu = P.ep.act == ACT_GLU;
+  const int n_cols = glu ? P.n : P.n;
+  if (ncol >= n_cols || row >= P.m_rows) return;
+  auto dot = [&](int wcol) {
+    float acc = 0.f;
+    for (int tap = 0; tap < P.taps; ++tap) {
+      const long long ar = static_cast<long long>(row) + P.tap_off0 + tap * P.tap_stride;
+      if (ar < 0 || ar >= a_rows) continue;
+      const bf16* ah = a_hi + ar * a_ld;
+      const bf16* al = a_lo ? a_lo + ar * a_ld : nullptr;
+      const long long wr = (static_cast<long long>(tap) * P.n_pad + wcol) * k_pad;
+      for (int c = 0; c < a_cols; ++c) {
+        float x = __bfloat162float(ah[c]), w = __bfloat162float(w_hi[wr + c]);
+        acc += x * w;
+        if (al) acc += __bfloat162float(al[c]) * w + x * __bfloat162float(w_lo[wr + c]);
+      }
+    }
+    return acc;
+  };
+  const ConvGemmEpilogue& ep = P.ep;
+  float v[1];
+  long long orow = row;
+  int ocol = ncol;
+  int n_limit = P.n;
+  if (glu) {
+    const int half = block_n / 2;
+    const int t = ncol / half, i = ncol % half;  // output column ncol lives in weight tile t
+    const int ca = t * block_n + i, cb = ca + half;
+    float a = dot(ca) + (ep.bias ? ep.bias[ca] : 0.f);
+    float g = dot(cb) + (ep.bias ? ep.bias[cb] : 0.f);
+    v[0] = a * (1.0f / (1.0f + __expf(-g))) * ep.scale;
+  } else {
+    if (P.up_s > 0) {
+      const int q = ncol / P.up_cout;
+      orow = static_cast<long long>(row) * P.up_s + q - P.up_p;
+      ocol = ncol - q * P.up_cout;
+      n_limit = P.up_cout;
+    }
+    float x = dot(ncol);
+    if (ep.bias) x += ep.bias[P.up_s > 0 ? ocol : ncol];
+    v[0] = apply_act(x, ep.act, ep.slope) * ep.scale;
+  }
+  bool valid = orow >= 0 && orow < P.out_rows;
+  if (valid && P.frame_mask) valid = P.frame_mask[orow / P.rate] != 0;
+  if (!valid) return;
+  store_row_segment<1>(ep, v, orow, ocol, n_limit);
+}
+
+int conv_gemm_simt_debug(const ConvGemmProblem& p, cudaStream_t stream) {
+  JB_PROPAGATE(validate(p));
+  KernelParams kp;
+  kp.taps = p.taps;
+  kp.k_chunks = p.k_pad / BLOCK_K;
+  kp.n_pad = p.n_pad;
+  kp.tap_off0 = p.tap_off0;
+  kp.tap_stride = p.tap_stride;
+  kp.n = p.n;
+  kp.m_rows = p.m_rows;
+  kp.num_m_tiles = 0;
+  kp.num_n_tiles = 0;
+  kp.frame_mask = p.frame_mask;
+  kp.rate = p.rate > 0 ? p.rate : 1;
+  kp.out_rows = p.out_rows;
+  kp.up_s = p.up_s;
+  kp.up_p = p.up_p;
+  kp.up_cout = p.up_cout > 0 ? p.up_cout : 1;
+  kp.ep = p.ep;
+  if (p.m_rows == 0) return 0;
+  dim3 grid(ceil_div(p.n, 128), p.m_rows);
+  conv_gemm_simt_kernel<<<grid, 128, 0, stream>>>(p.a_hi, p.a_lo, p.a_rows, p.a_ld, p.w_hi, p.w_lo, p.k_pad,
+                                                  p.a_cols > 0 ? p.a_cols : p.k_pad, p.block_n, kp);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+}  // namespace jb

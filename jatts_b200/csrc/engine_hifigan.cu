@@ -1,0 +1,266 @@
+// HiFi-GAN V1 generator engine: batched, B200-native restatement of
+// parallel_wavegan HiFiGANGenerator.inference() as reached from jatts/vocoder/vocoder.py:64
+// (architecture: oracle/hifigan.py header).  All Conv1d / ConvTranspose1d layers are tcgen05
+// implicit GEMMs over the packed-with-gaps channels-last layout with bf16 operands and fp32 TMEM
+// accumulation; LeakyReLU, bias, residual add, the MRF branch mean and the next layer's operand
+// conversion are fused into the epilogues.  ConvTranspose1d(k = 2s, stride s) is a 2-tap polyphase
+// GEMM with N = s * C_out whose epilogue scatters phase q of input row j to output row j*s + q - p.
+#include "engine_common.cuh"
+
+using namespace jb;
+
+struct jatts_hifigan {
+  jatts_hifigan_config cfg;
+  int device = 0;
+  WeightTable wt;
+  ConvW input_conv;
+  std::vector<ConvW> ups;
+  std::vector<std::vector<std::vector<ConvW>>> c1, c2;  // [stage][block][dilation]
+  const float *out_w, *mel_scale, *mel_shift;
+  float out_b = 0.f;
+  int hop = 1;
+  std::vector<int> rate, chans;  // per stage output rate / channels
+
+  Arena arena;
+  int cap_rows = 0, cap_utt = 0;
+  bf16 *mel, *x0, *xa0, *x, *xa, *t, *y[2];
+  float* sum;
+  uint8_t* mask;
+  int *seg, *d_small = nullptr, *h_small = nullptr;
+  cudaEvent_t staged = nullptr;
+  bool staged_pending = false;
+};
+
+namespace jb {
+
+static int ensure_workspace(jatts_hifigan* h, int rows, int n_utt) {
+  if (n_utt > h->cap_utt) {
+    const int cu = round_up(n_utt, 64);
+    if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->d_small) cudaFree(h->d_small);
+    h->h_small = nullptr; h->d_small = nullptr;
+    JB_CUDA_OK(cudaMallocHost(&h->h_small, sizeof(int) * 3 * cu));
+    JB_CUDA_OK(cudaMalloc(&h->d_small, sizeof(int) * 3 * cu));
+    h->cap_utt = cu;
+  }
+  if (rows <= h->cap_rows) return 0;
+  const jatts_hifigan_config& c = h->cfg;
+  const size_t R = round_up(rows + 64, 256);
+  size_t per_row = static_cast<size_t>(c.channels);  // stage input of stage 0: [rows, channels]
+  for (size_t i = 0; i < h->rate.size(); ++i) per_row = std::max(per_row, static_cast<size_t>(h->rate[i]) * h->chans[i]);
+  const size_t in_pad = round_up(c.in_channels, 64);
+  size_t bytes = Arena::padded(2 * R * in_pad) + 7 * Arena::padded(2 * R * per_row) + Arena::padded(4 * R * per_row) +
+                 Arena::padded(R) + Arena::padded(4 * R);
+  JB_PROPAGATE(h->arena.reserve(bytes));
+  Arena& a = h->arena;
+  a.reset();
+  h->mel = a.take<bf16>(R * in_pad);
+  h->x0 = a.take<bf16>(R * per_row); h->xa0 = a.take<bf16>(R * per_row);
+  h->x = a.take<bf16>(R * per_row); h->xa = a.take<bf16>(R * per_row);
+  h->t = a.take<bf16>(R * per_row);
+  h->y[0] = a.take<bf16>(R * per_row); h->y[1] = a.take<bf16>(R * per_row);
+  h->sum = a.take<float>(R * per_row);
+  h->mask = a.take<uint8_t>(R);
+  h->seg = a.take<int>(R);
+  h->cap_rows = static_cast<int>(R);
+  return 0;
+}
+
+struct StageIO {
+  const uint8_t* mask;
+  int rate;       // rows per mel frame of the tensors this conv reads and writes
+  long long rows; // rows at that rate
+};
+
+static int run_conv(const ConvW& w, const bf16* a, int a_cols, const StageIO& io, int dilation, ConvGemmEpilogue ep,
+                    cudaStream_t s) {
+  ConvGemmProblem p{};
+  p.a_hi = a; p.a_lo = nullptr; p.a_rows = static_cast<int>(io.rows); p.a_ld = a_cols; p.a_cols = a_cols;
+  p.w_hi = w.hi; p.w_lo = nullptr; p.taps = w.taps; p.n_pad = w.n_pad; p.k_pad = w.k_pad;
+  p.tap_off0 = -((w.taps - 1) / 2) * dilation; p.tap_stride = dilation;
+  p.n = w.n; p.m_rows = static_cast<int>(io.rows); p.block_n = w.block_n;
+  p.frame_mask = io.mask; p.rate = io.rate; p.out_rows = static_cast<int>(io.rows);
+  ep.bias = w.bias;
+  if (ep.scale == 0.f) ep.scale = 1.f;
+  if (ep.post_scale == 0.f) ep.post_scale = 1.f;
+  p.ep = ep;
+  return conv_gemm_tc(p, s);
+}
+
+}  // namespace jb
+
+extern "C" int jatts_hifigan_create(const jatts_hifigan_config* cfg, const jatts_tensor* weights, int32_t n_weights,
+                                    jatts_hifigan** out) {
+  JB_REQUIRE(cfg && weights && out, JATTS_E_INVALID, "hifigan_create: null argument");
+  JB_REQUIRE(cfg->out_channels == 1, JATTS_E_UNSUPPORTED, "only out_channels == 1 is implemented");
+  JB_REQUIRE(cfg->n_upsamples >= 1 && cfg->n_upsamples <= 8 && cfg->n_resblocks >= 1 && cfg->n_resblocks <= 8 &&
+                 cfg->n_dilations >= 1 && cfg->n_dilations <= 8,
+             JATTS_E_INVALID, "hifigan_create: bad stage/block counts");
+  JB_REQUIRE(cfg->channels % (1 << cfg->n_upsamples) == 0 && (cfg->channels >> cfg->n_upsamples) % 32 == 0,
+             JATTS_E_UNSUPPORTED, "every stage needs a channel count that is a multiple of 32");
+  JB_REQUIRE((cfg->kernel_size & 1) == 1, JATTS_E_UNSUPPORTED, "kernel_size must be odd");
+  jatts_hifigan* h = new jatts_hifigan();
+  h->cfg = *cfg;
+  auto fail = [&](int rc) { delete h; return rc; };
+  if (cudaGetDevice(&h->device) != cudaSuccess) { set_last_error("cudaGetDevice failed (no CUDA device?)"); return fail(JATTS_E_CUDA); }
+  int rc = h->wt.init(weights, n_weights);
+  if (rc) return fail(rc);
+  if ((rc = load_conv(h->wt, "input_conv", cfg->kernel_size, cfg->channels, cfg->in_channels, false, true, cfg->channels, &h->input_conv))) return fail(rc);
+  int r = 1;
+  h->ups.resize(cfg->n_upsamples);
+  h->c1.resize(cfg->n_upsamples);
+  h->c2.resize(cfg->n_upsamples);
+  for (int i = 0; i < cfg->n_upsamples; ++i) {
+    const int s = cfg->upsample_scales[i];
+    const int ci = cfg->channels >> i, co = cfg->channels >> (i + 1);
+    if (s < 1) { set_last_error("upsample scale < 1"); return fail(JATTS_E_INVALID); }
+    r *= s;
+    h->rate.push_back(r);
+    h->chans.push_back(co);
+    if ((rc = load_conv(h->wt, "ups" + std::to_string(i), 2, s * co, ci, false, true, s * co, &h->ups[i]))) return fail(rc);
+    h->c1[i].resize(cfg->n_resblocks);
+    h->c2[i].resize(cfg->n_resblocks);
+    for (int j = 0; j < cfg->n_resblocks; ++j) {
+      const int k = cfg->resblock_kernels[j];
+      if ((k & 1) == 0) { set_last_error("resblock kernel must be odd"); return fail(JATTS_E_UNSUPPORTED); }
+      h->c1[i][j].resize(cfg->n_dilations);
+      h->c2[i][j].resize(cfg->n_dilations);
+      for (int d = 0; d < cfg->n_dilations; ++d) {
+        const std::string p = "rb" + std::to_string(i) + "_" + std::to_string(j);
+        if ((rc = load_conv(h->wt, p + ".c1_" + std::to_string(d), k, co, co, false, true, co, &h->c1[i][j][d]))) return fail(rc);
+        if ((rc = load_conv(h->wt, p + ".c2_" + std::to_string(d), k, co, co, false, true, co, &h->c2[i][j][d]))) return fail(rc);
+        // the gap between utterances must cover the widest receptive field at this rate
+        if ((k - 1) / 2 * cfg->resblock_dilations[j][d] > kGapRows * r) {
+          set_last_error("dilated receptive field exceeds the inter-utterance gap");
+          return fail(JATTS_E_UNSUPPORTED);
+        }
+      }
+    }
+  }
+  h->hop = r;
+  const int cl = cfg->channels >> cfg->n_upsamples;
+  if ((rc = h->wt.f32("output.w", static_cast<long long>(cfg->kernel_size) * cl, &h->out_w))) return fail(rc);
+  const float* ob;
+  if ((rc = h->wt.f32("output.b", 1, &ob))) return fail(rc);
+  if (cudaMemcpy(&h->out_b, ob, sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) { set_last_error("cudaMemcpy(output.b) failed"); return fail(JATTS_E_CUDA); }
+  if ((rc = h->wt.f32("mel_scale", cfg->in_channels, &h->mel_scale))) return fail(rc);
+  if ((rc = h->wt.f32("mel_shift", cfg->in_channels, &h->mel_shift))) return fail(rc);
+  if (cudaEventCreateWithFlags(&h->staged, cudaEventDisableTiming) != cudaSuccess) { set_last_error("cudaEventCreate failed"); return fail(JATTS_E_CUDA); }
+  *out = h;
+  return 0;
+}
+
+extern "C" void jatts_hifigan_destroy(jatts_hifigan* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  h->arena.release();
+  if (h->h_small) cudaFreeHost(h->h_small);
+  if (h->d_small) cudaFree(h->d_small);
+  if (h->staged) cudaEventDestroy(h->staged);
+  delete h;
+}
+
+extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int32_t* h_mel_lens, int32_t n_utt,
+                                 float* d_wave, void* stream) {
+  JB_REQUIRE(h && d_mel && h_mel_lens && d_wave && n_utt > 0, JATTS_E_INVALID, "hifigan_run: bad argument");
+  JB_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const jatts_hifigan_config& c = h->cfg;
+  for (int i = 0; i < n_utt; ++i) JB_REQUIRE(h_mel_lens[i] > 0, JATTS_E_INVALID, "every clip needs >= 1 frame");
+  HostLayout hl;
+  hl.build(h_mel_lens, n_utt);
+  JB_REQUIRE(static_cast<long long>(hl.n_rows) * h->hop < (1ll << 31), JATTS_E_UNSUPPORTED,
+             "batch too large for 32-bit row indices; split it");
+  JB_PROPAGATE(ensure_workspace(h, hl.n_rows, n_utt));
+  // stage the layout tables (pinned buffer is reused: wait for the previous call's copy first)
+  if (h->staged_pending) JB_CUDA_OK(cudaEventSynchronize(h->staged));
+  const int cu = h->cap_utt;
+  for (int i = 0; i < n_utt; ++i) {
+    h->h_small[i] = hl.seg_start[i];
+    h->h_small[cu + i] = hl.seg_len[i];
+    h->h_small[2 * cu + i] = hl.off[i];
+  }
+  JB_CUDA_OK(cudaMemcpyAsync(h->d_small, h->h_small, sizeof(int) * 3 * cu, cudaMemcpyHostToDevice, s));
+  JB_CUDA_OK(cudaEventRecord(h->staged, s));
+  h->staged_pending = true;
+  RowLayout L;
+  L.seg_start = h->d_small; L.seg_len = h->d_small + cu; L.frame_mask = h->mask; L.frame_seg = h->seg;
+  L.nseg = n_utt; L.n_rows = hl.n_rows;
+  const int* d_off = h->d_small + 2 * cu;
+  JB_PROPAGATE(fill_layout(L.seg_start, L.seg_len, n_utt, hl.n_rows, h->mask, h->seg, s));
+
+  const int in_pad = round_up(c.in_channels, 64);
+  const float slope = c.lrelu_slope;
+  // mel re-normalisation (vocoder.py:57-61) fused into the operand conversion
+  JB_PROPAGATE(zero_gap_rows(h->mel, in_pad * 2, h->mask, 1, hl.n_rows, s));
+  JB_PROPAGATE(pack_mel_affine(d_mel, c.in_channels, h->mel_scale, h->mel_shift, L, d_off, h->mel, in_pad, s));
+  StageIO io{h->mask, 1, hl.n_rows};
+  int cur = 0;  // y[cur] holds leaky_relu(stage input)
+  {
+    JB_PROPAGATE(zero_gap_rows(h->y[cur], c.channels * 2, h->mask, 1, io.rows, s));
+    ConvGemmEpilogue e{};
+    e.out_act = h->y[cur]; e.out_act_slope = slope; e.out_act_ld = c.channels;
+    JB_PROPAGATE(run_conv(h->input_conv, h->mel, in_pad, io, 1, e, s));
+  }
+  int c_in = c.channels;
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    const int sc = c.upsample_scales[i];
+    const int co = h->chans[i];
+    const StageIO in_io = io;
+    io.rate = h->rate[i];
+    io.rows = static_cast<long long>(hl.n_rows) * io.rate;
+    const int nxt = cur ^ 1;
+    // operand buffers of this stage: gap rows must be zero at this rate
+    bf16* operands[] = {h->xa0, h->xa, h->t, h->y[nxt]};
+    for (bf16* b : operands) JB_PROPAGATE(zero_gap_rows(b, co * 2, h->mask, io.rate, io.rows, s));
+    {
+      // ConvTranspose1d as a 2-tap polyphase GEMM: tap 0 reads x[j], tap 1 reads x[j-1]
+      const ConvW& w = h->ups[i];
+      ConvGemmProblem p{};
+      p.a_hi = h->y[cur]; p.a_rows = static_cast<int>(in_io.rows); p.a_ld = c_in; p.a_cols = c_in;
+      p.w_hi = w.hi; p.taps = 2; p.n_pad = w.n_pad; p.k_pad = w.k_pad; p.tap_off0 = 0; p.tap_stride = -1;
+      p.n = w.n; p.m_rows = static_cast<int>(in_io.rows); p.block_n = w.block_n;
+      p.frame_mask = h->mask; p.rate = io.rate; p.out_rows = static_cast<int>(io.rows);
+      p.up_s = sc; p.up_p = sc / 2 + sc % 2; p.up_cout = co;
+      ConvGemmEpilogue e{};
+      e.bias = w.bias; e.scale = 1.f; e.post_scale = 1.f;
+      e.out_hi = h->x0; e.out_bf_ld = co; e.out_act = h->xa0; e.out_act_slope = slope; e.out_act_ld = co;
+      p.ep = e;
+      JB_PROPAGATE(conv_gemm_tc(p, s));
+    }
+    const bool last_stage = i == c.n_upsamples - 1;
+    const float next_slope = last_stage ? 0.01f : slope;  // torch.nn.LeakyReLU() default before output_conv
+    for (int j = 0; j < c.n_resblocks; ++j) {
+      const bf16* x_res = h->x0;
+      const bf16* xa = h->xa0;
+      for (int d = 0; d < c.n_dilations; ++d) {
+        ConvGemmEpilogue e1{};
+        e1.act = ACT_LRELU; e1.slope = slope; e1.out_hi = h->t; e1.out_bf_ld = co;
+        JB_PROPAGATE(run_conv(h->c1[i][j][d], xa, co, io, c.resblock_dilations[j][d], e1, s));
+        ConvGemmEpilogue e2{};
+        e2.res_bf16 = x_res; e2.res_ld = co;
+        if (d + 1 < c.n_dilations) {
+          e2.out_hi = h->x; e2.out_bf_ld = co; e2.out_act = h->xa; e2.out_act_slope = slope; e2.out_act_ld = co;
+        } else {
+          // branch output: accumulate the mean over residual blocks; the last block emits the next
+          // layer's operand leaky_relu(mean) directly
+          e2.out_f32_ld = co;
+          if (j > 0) e2.accum_in = h->sum;
+          if (j + 1 < c.n_resblocks) {
+            e2.out_f32 = h->sum;
+          } else {
+            e2.post_scale = 1.0f / c.n_resblocks;
+            e2.out_act = h->y[nxt]; e2.out_act_slope = next_slope; e2.out_act_ld = co;
+          }
+        }
+        JB_PROPAGATE(run_conv(h->c2[i][j][d], h->t, co, io, 1, e2, s));
+        x_res = h->x;
+        xa = h->xa;
+      }
+    }
+    cur = nxt;
+    c_in = co;
+  }
+  JB_PROPAGATE(output_conv_tanh(h->y[cur], c_in, c_in, h->out_w, h->out_b, c.kernel_size, L, h->hop, d_off, d_wave, s));
+  return 0;
+}

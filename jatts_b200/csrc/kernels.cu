@@ -1,0 +1,678 @@
+// Bandwidth-bound / small kernels of the synthesis path (CUDA cores, fp32 arithmetic).
+// Every kernel works on the packed-with-gaps row layout (common.cuh): gap rows are never written.
+#include "kernels.cuh"
+
+namespace jb {
+
+// ------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_layout_kernel(const int* __restrict__ seg_start, const int* __restrict__ seg_len, int nseg,
+                                   int n_rows, uint8_t* __restrict__ mask, int* __restrict__ seg) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int lo = 0, hi = nseg - 1, b = -1;
+  while (lo <= hi) {  // last segment with start <= r
+    const int mid = (lo + hi) >> 1;
+    if (seg_start[mid] <= r) { b = mid; lo = mid + 1; } else { hi = mid - 1; }
+  }
+  const bool v = b >= 0 && r < seg_start[b] + seg_len[b];
+  mask[r] = v ? 1 : 0;
+  seg[r] = v ? b : -1;
+}
+int fill_layout(const int* seg_start, const int* seg_len, int nseg, int n_rows, uint8_t* frame_mask, int* frame_seg,
+                cudaStream_t s) {
+  if (n_rows == 0) return 0;
+  fill_layout_kernel<<<ceil_div(n_rows, 256), 256, 0, s>>>(seg_start, seg_len, nseg, n_rows, frame_mask, frame_seg);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+__global__ void zero_gap_rows_kernel(uint4* __restrict__ buf, int row_vec, const uint8_t* __restrict__ mask, int rate,
+                                     long long rows) {
+  const long long r = blockIdx.x;
+  if (r >= rows || mask[r / rate]) return;
+  uint4* p = buf + r * row_vec;
+  for (int i = threadIdx.x; i < row_vec; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+}
+int zero_gap_rows(void* buf, int row_bytes, const uint8_t* frame_mask, int rate, long long rows, cudaStream_t s) {
+  JB_REQUIRE(row_bytes % 16 == 0, -2, "zero_gap_rows: row_bytes % 16");
+  if (rows == 0) return 0;
+  JB_REQUIRE(rows < (1ll << 31), -2, "zero_gap_rows: too many rows");
+  zero_gap_rows_kernel<<<static_cast<unsigned>(rows), 64, 0, s>>>(static_cast<uint4*>(buf), row_bytes / 16,
+                                                                  frame_mask, rate, rows);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_tokens_kernel(const long long* __restrict__ tokens, const int* __restrict__ tok_off,
+                                    const float* __restrict__ emb, int vocab, int d, float scale, RowLayout L,
+                                    float* __restrict__ x) {
+  const int r = blockIdx.x;
+  const int b = L.frame_seg[r];
+  if (b < 0) return;
+  long long tok = tokens[tok_off[b] + (r - L.seg_start[b])];
+  if (tok < 0 || tok >= vocab) tok = 0;  // host validates ids; never index out of the table
+  const float4* e = reinterpret_cast<const float4*>(emb + tok * d);
+  float4* o = reinterpret_cast<float4*>(x + static_cast<long long>(r) * d);
+  for (int i = threadIdx.x; i < d / 4; i += blockDim.x) {
+    float4 v = e[i];
+    o[i] = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+  }
+}
+int embed_tokens(const long long* tokens, const int* tok_off, const float* emb, int vocab, int d, float scale,
+                 RowLayout L, float* x, cudaStream_t s) {
+  JB_REQUIRE(d % 4 == 0, -2, "embed: d % 4");
+  if (L.n_rows == 0) return 0;
+  embed_tokens_kernel<<<L.n_rows, 96, 0, s>>>(tokens, tok_off, emb, vocab, d, scale, L, x);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (one warp per row, two-pass in registers)
+// ------------------------------------------------------------------------------------------------
+static constexpr int LN_MAXV = 4;  // float4 per lane -> C <= 512
+
+template <bool DOT>
+__global__ void layernorm_kernel(const float* __restrict__ x, int c, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, RowLayout L, float* __restrict__ y,
+                                 bf16* __restrict__ hi, bf16* __restrict__ lo, int bf_ld,
+                                 const float* __restrict__ w, float wb, float* __restrict__ dot_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= L.n_rows || !L.frame_mask[warp]) return;
+  const long long r = warp;
+  const int nv = c >> 2;  // float4 count
+  float4 v[LN_MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nv) {
+      v[i] = reinterpret_cast<const float4*>(x + r * c)[j];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / c;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / c + eps);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nv) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[j];
+      const float4 bb = reinterpret_cast<const float4*>(beta)[j];
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+      o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+      o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+      o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+      if (DOT) {
+        const float4 ww = reinterpret_cast<const float4*>(w)[j];
+        dot += (o.x * ww.x + o.y * ww.y) + (o.z * ww.z + o.w * ww.w);
+      } else {
+        if (y) reinterpret_cast<float4*>(y + r * c)[j] = o;
+        if (hi) {
+          bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+          split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
+          __nv_bfloat162 p0 = __halves2bfloat162(h0, h1), p1 = __halves2bfloat162(h2, h3);
+          uint2 ph = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+          reinterpret_cast<uint2*>(hi + r * bf_ld)[j] = ph;
+          if (lo) {
+            __nv_bfloat162 q0 = __halves2bfloat162(l0, l1), q1 = __halves2bfloat162(l2, l3);
+            uint2 pl = make_uint2(*reinterpret_cast<uint32_t*>(&q0), *reinterpret_cast<uint32_t*>(&q1));
+            reinterpret_cast<uint2*>(lo + r * bf_ld)[j] = pl;
+          }
+        }
+      }
+    }
+  }
+  if (DOT) {
+    dot = warp_sum(dot);
+    if (lane == 0) dot_out[r] = dot + wb;
+  }
+}
+int layernorm_rows(const float* x, int c, const float* gamma, const float* beta, float eps, RowLayout L, float* y,
+                   bf16* hi, bf16* lo, int bf_ld, cudaStream_t s) {
+  JB_REQUIRE(c % 4 == 0 && c <= 128 * LN_MAXV, -2, "layernorm: C must be a multiple of 4 and <= 512");
+  JB_REQUIRE(bf_ld % 4 == 0, -2, "layernorm: bf_ld % 4");
+  if (L.n_rows == 0) return 0;
+  layernorm_kernel<false><<<ceil_div(L.n_rows, 8), 256, 0, s>>>(x, c, gamma, beta, eps, L, y, hi, lo, bf_ld, nullptr,
+                                                                0.f, nullptr);
+  JB_KERNEL_OK();
+  return 0;
+}
+int ln_dot_rows(const float* x, int c, const float* gamma, const float* beta, float eps, const float* w, float b,
+                RowLayout L, float* out, cudaStream_t s) {
+  JB_REQUIRE(c % 4 == 0 && c <= 128 * LN_MAXV, -2, "ln_dot: C must be a multiple of 4 and <= 512");
+  if (L.n_rows == 0) return 0;
+  layernorm_kernel<true><<<ceil_div(L.n_rows, 8), 256, 0, s>>>(x, c, gamma, beta, eps, L, nullptr, nullptr, nullptr, 4,
+                                                               w, b, out);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+__global__ void split_rows_kernel(const float* __restrict__ x, int c, RowLayout L, bf16* __restrict__ hi,
+                                  bf16* __restrict__ lo, int bf_ld) {
+  const int r = blockIdx.x;
+  if (!L.frame_mask[r]) return;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    bf16 h, l;
+    split_bf16(x[static_cast<long long>(r) * c + i], h, l);
+    hi[static_cast<long long>(r) * bf_ld + i] = h;
+    lo[static_cast<long long>(r) * bf_ld + i] = l;
+  }
+}
+int split_rows(const float* x, int c, RowLayout L, bf16* hi, bf16* lo, int bf_ld, cudaStream_t s) {
+  if (L.n_rows == 0) return 0;
+  split_rows_kernel<<<L.n_rows, 128, 0, s>>>(x, c, L, hi, lo, bf_ld);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// legacy relative-position attention (attention.py:164-206), fp32 on CUDA cores.
+//
+// One CTA = (query tile of R rows, utterance, head).  With BD[a,n] = (q_a + v) . p_n the reference's
+// rel_shift (attention.py:142-162) has the closed form
+//     shifted[a,b] = BD[a, T-1-a+b]   (b <= a),   0 (b == a+1),   BD[a+1, b-a-2]   (b > a+1)
+// so score row a needs q_a against keys and against p, and q_{a+1} against p.
+// ------------------------------------------------------------------------------------------------
+static constexpr int ATT_TK = 64;       // keys / positions per smem tile
+static constexpr int ATT_THREADS = 256;
+
+template <int R>
+__global__ void __launch_bounds__(ATT_THREADS)
+relpos_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ pos, const float* __restrict__ bias_u,
+                        const float* __restrict__ bias_v, int d_model, int dk, RowLayout L, int t_pad,
+                        bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int out_ld) {
+  constexpr int RPT = R / 4;  // query rows per thread
+  const int b = blockIdx.y, h = blockIdx.z;
+  const int T = L.seg_len[b];
+  const int a0 = blockIdx.x * R;
+  if (a0 >= T) return;
+  const long long base = L.seg_start[b];
+  const int ks = dk + 4;  // padded smem row stride (floats): conflict-free LDS.128
+  extern __shared__ float sm[];
+  float* qu = sm;                    // [R][dk]
+  float* qv = qu + R * dk;           // [R+1][dk]
+  float* S = qv + (R + 1) * dk;      // [R][t_pad]
+  float* tile = S + R * t_pad;       // [ATT_TK][ks]
+  const int tid = threadIdx.x;
+  const int tx = tid & 63, ty = tid >> 6;
+  const int ld3 = 3 * d_model;
+  const int dk4 = dk >> 2;
+
+  for (int i = tid; i < (R + 1) * dk; i += ATT_THREADS) {
+    const int r = i / dk, d = i - r * dk;
+    const int a = a0 + r;
+    float q = 0.f;
+    if (a < T) q = qkv[(base + a) * ld3 + h * dk + d];
+    if (r < R) qu[r * dk + d] = (a < T) ? q + bias_u[h * dk + d] : 0.f;
+    qv[r * dk + d] = (a < T) ? q + bias_v[h * dk + d] : 0.f;
+  }
+  __syncthreads();
+
+  // ---- phase A: S[r][key] = (q_a + u) . k_key
+  for (int k0 = 0; k0 < T; k0 += ATT_TK) {
+    for (int i = tid; i < ATT_TK * dk4; i += ATT_THREADS) {
+      const int kk = i / dk4, d4 = i - kk * dk4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + kk < T) v = *reinterpret_cast<const float4*>(qkv + (base + k0 + kk) * ld3 + d_model + h * dk + d4 * 4);
+      *reinterpret_cast<float4*>(tile + kk * ks + d4 * 4) = v;
+    }
+    __syncthreads();
+    float acc[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) acc[i] = 0.f;
+    const float* kr = tile + tx * ks;
+    for (int d = 0; d < dk; d += 4) {
+      const float4 kv = *reinterpret_cast<const float4*>(kr + d);
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(qu + (ty * RPT + i) * dk + d);
+        acc[i] += (q.x * kv.x + q.y * kv.y) + (q.z * kv.z + q.w * kv.w);
+      }
+    }
+    if (k0 + tx < T) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) S[(ty * RPT + i) * t_pad + k0 + tx] = acc[i];
+    }
+    __syncthreads();
+  }
+
+  // ---- phase B: add the shifted positional term
+  for (int n0 = 0; n0 < T; n0 += ATT_TK) {
+    for (int i = tid; i < ATT_TK * dk4; i += ATT_THREADS) {
+      const int kk = i / dk4, d4 = i - kk * dk4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + kk < T) v = *reinterpret_cast<const float4*>(pos + static_cast<long long>(n0 + kk) * d_model + h * dk + d4 * 4);
+      *reinterpret_cast<float4*>(tile + kk * ks + d4 * 4) = v;
+    }
+    __syncthreads();
+    float acc[RPT + 1];
+#pragma unroll
+    for (int i = 0; i <= RPT; ++i) acc[i] = 0.f;
+    const float* pr = tile + tx * ks;
+    for (int d = 0; d < dk; d += 4) {
+      const float4 pv = *reinterpret_cast<const float4*>(pr + d);
+#pragma unroll
+      for (int i = 0; i <= RPT; ++i) {
+        const float4 q = *reinterpret_cast<const float4*>(qv + (ty * RPT + i) * dk + d);
+        acc[i] += (q.x * pv.x + q.y * pv.y) + (q.z * pv.z + q.w * pv.w);
+      }
+    }
+    const int n = n0 + tx;
+    if (n < T) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = ty * RPT + i;
+        const int a = a0 + r;
+        if (a < T) {
+          const int b1 = n - (T - 1 - a);
+          if (b1 >= 0 && b1 <= a) S[r * t_pad + b1] += acc[i];
+          const int b2 = n + a + 2;
+          if (b2 < T) S[r * t_pad + b2] += acc[i + 1];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase C: softmax over keys (scores / sqrt(dk))
+  {
+    const float scale = rsqrtf(static_cast<float>(dk));
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < R; r += ATT_THREADS / 32) {
+      if (a0 + r >= T) continue;
+      float* row = S + r * t_pad;
+      float m = -INFINITY;
+      for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
+      m = warp_max(m) * scale;
+      float sum = 0.f;
+      for (int j = lane; j < T; j += 32) {
+        const float e = expf(row[j] * scale - m);
+        row[j] = e;
+        sum += e;
+      }
+      const float inv = 1.0f / warp_sum(sum);
+      for (int j = lane; j < T; j += 32) row[j] *= inv;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase D: ctx = P . V
+  float ctx[RPT][4];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
+  for (int k0 = 0; k0 < T; k0 += ATT_TK) {
+    for (int i = tid; i < ATT_TK * dk4; i += ATT_THREADS) {
+      const int kk = i / dk4, d4 = i - kk * dk4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + kk < T) v = *reinterpret_cast<const float4*>(qkv + (base + k0 + kk) * ld3 + 2 * d_model + h * dk + d4 * 4);
+      *reinterpret_cast<float4*>(tile + kk * ks + d4 * 4) = v;
+    }
+    __syncthreads();
+    const int kn = min(ATT_TK, T - k0);
+    for (int kk = 0; kk < kn; ++kk) {
+      float p[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) p[i] = S[(ty * RPT + i) * t_pad + k0 + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = tx + 64 * j;
+        if (d < dk) {
+          const float v = tile[kk * ks + d];
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) ctx[i][j] += p[i] * v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int a = a0 + ty * RPT + i;
+    if (a >= T) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = tx + 64 * j;
+      if (d < dk) {
+        bf16 hh, ll;
+        split_bf16(ctx[i][j], hh, ll);
+        out_hi[(base + a) * out_ld + h * dk + d] = hh;
+        if (out_lo) out_lo[(base + a) * out_ld + h * dk + d] = ll;
+      }
+    }
+  }
+}
+
+template <int R>
+static int launch_attention(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
+                            int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld,
+                            cudaStream_t s) {
+  const int dk = d_model / n_head;
+  const int t_pad = round_up(max_len, 4) + 4;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(R) * dk + (R + 1) * dk + static_cast<size_t>(R) * t_pad +
+                                       ATT_TK * (dk + 4));
+  JB_REQUIRE(smem <= 227 * 1024, -2, "attention: utterance too long for shared memory");
+  auto kern = relpos_attention_kernel<R>;
+  JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(ceil_div(max_len, R), L.nseg, n_head);
+  kern<<<grid, ATT_THREADS, smem, s>>>(qkv, pos, bias_u, bias_v, d_model, dk, L, t_pad, out_hi, out_lo, out_ld);
+  JB_KERNEL_OK();
+  return 0;
+}
+int relpos_attention(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
+                     int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s) {
+  const int dk = d_model / n_head;
+  JB_REQUIRE(dk * n_head == d_model && dk % 4 == 0 && dk <= 256, -2, "attention: d_k must be a multiple of 4, <= 256");
+  if (L.nseg == 0 || max_len == 0) return 0;
+  if (max_len <= 1800) return launch_attention<16>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
+  if (max_len <= 4000) return launch_attention<8>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
+  return launch_attention<4>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise conv + folded BatchNorm + Swish
+// ------------------------------------------------------------------------------------------------
+__global__ void dwconv_swish_kernel(const float* __restrict__ g, int c, const float* __restrict__ wT,
+                                    const float* __restrict__ bias, int k, RowLayout L, bf16* __restrict__ out_hi,
+                                    bf16* __restrict__ out_lo, int out_ld) {
+  const int r = blockIdx.x;
+  const int b = L.frame_seg[r];
+  if (b < 0) return;
+  const int s0 = L.seg_start[b], s1 = s0 + L.seg_len[b];
+  const int pad = (k - 1) / 2;
+  for (int c4 = threadIdx.x; c4 < c / 4; c4 += blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(bias)[c4];
+    for (int j = 0; j < k; ++j) {
+      const int rr = r + j - pad;
+      if (rr < s0 || rr >= s1) continue;
+      const float4 x = reinterpret_cast<const float4*>(g + static_cast<long long>(rr) * c)[c4];
+      const float4 w = reinterpret_cast<const float4*>(wT + j * c)[c4];
+      acc.x += x.x * w.x; acc.y += x.y * w.y; acc.z += x.z * w.z; acc.w += x.w * w.w;
+    }
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+    bf16 hh[4], ll[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float y = o[i] * (1.0f / (1.0f + expf(-o[i])));  // swish.py:13-18
+      split_bf16(y, hh[i], ll[i]);
+    }
+    __nv_bfloat162 p0 = __halves2bfloat162(hh[0], hh[1]), p1 = __halves2bfloat162(hh[2], hh[3]);
+    reinterpret_cast<uint2*>(out_hi + static_cast<long long>(r) * out_ld)[c4] =
+        make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+    if (out_lo) {
+      __nv_bfloat162 q0 = __halves2bfloat162(ll[0], ll[1]), q1 = __halves2bfloat162(ll[2], ll[3]);
+      reinterpret_cast<uint2*>(out_lo + static_cast<long long>(r) * out_ld)[c4] =
+          make_uint2(*reinterpret_cast<uint32_t*>(&q0), *reinterpret_cast<uint32_t*>(&q1));
+    }
+  }
+}
+int dwconv_swish(const float* g, int c, const float* wT, const float* bias, int k, RowLayout L, bf16* out_hi,
+                 bf16* out_lo, int out_ld, cudaStream_t s) {
+  JB_REQUIRE(c % 4 == 0 && out_ld % 4 == 0 && (k & 1) == 1, -2, "dwconv: C % 4, odd k");
+  if (L.n_rows == 0) return 0;
+  dwconv_swish_kernel<<<L.n_rows, 96, 0, s>>>(g, c, wT, bias, k, L, out_hi, out_lo, out_ld);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// speaker embedding integration ("add")
+// ------------------------------------------------------------------------------------------------
+__global__ void add_speaker_kernel(const float* __restrict__ spembs, int spk_dim, const float* __restrict__ w,
+                                   const float* __restrict__ bvec, int d, RowLayout L, float* __restrict__ hs) {
+  extern __shared__ float sh[];  // [spk_dim] normalised embedding, then [d] projected
+  float* e = sh;
+  float* proj = sh + spk_dim;
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < spk_dim; i += blockDim.x) {
+    const float v = spembs[b * spk_dim + i];
+    e[i] = v;
+    ss += v * v;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+  const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);  // F.normalize eps (fastspeech2.py:752)
+  for (int o = threadIdx.x; o < d; o += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < spk_dim; ++i) acc += (e[i] * inv) * w[o * spk_dim + i];
+    proj[o] = acc + bvec[o];
+  }
+  __syncthreads();
+  const int s0 = L.seg_start[b], n = L.seg_len[b];
+  for (long long i = threadIdx.x; i < static_cast<long long>(n) * d; i += blockDim.x)
+    hs[static_cast<long long>(s0) * d + i] += proj[i % d];
+}
+int add_speaker(const float* spembs, int spk_dim, const float* w, const float* b, int d, RowLayout L, float* hs,
+                cudaStream_t s) {
+  if (L.nseg == 0) return 0;
+  add_speaker_kernel<<<L.nseg, 256, sizeof(float) * (spk_dim + d), s>>>(spembs, spk_dim, w, b, d, L, hs);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// durations + per-utterance inclusive scan (one warp per utterance)
+// ------------------------------------------------------------------------------------------------
+__global__ void durations_kernel(const float* __restrict__ logd, float alpha, RowLayout L,
+                                 const int* __restrict__ tok_off, long long* __restrict__ dur_out,
+                                 int* __restrict__ cum, int* __restrict__ n_frames) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int s0 = L.seg_start[b], T = L.seg_len[b];
+  // pass 1: predicted durations (duration_predictor.py:86-90), the regulator's alpha-scaled copy
+  // (length_regulator.py:81-83) and its exact integer total
+  int tot = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    int dl = 0;
+    if (t < T) {
+      const float dv = fmaxf(rintf(expf(logd[s0 + t]) - 1.0f), 0.0f);
+      dur_out[tok_off[b] + t] = static_cast<long long>(dv);
+      dl = (alpha != 1.0f) ? static_cast<int>(rintf(dv * alpha)) : static_cast<int>(dv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o);
+    tot += dl;
+  }
+  const bool all_zero = (tot == 0);  // length_regulator.py:86-94 with B == 1: every token becomes 1
+  int carry = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    int dl = 0;
+    if (t < T) {
+      if (all_zero) {
+        dl = 1;
+        if (alpha == 1.0f) dur_out[tok_off[b] + t] = 1;  // in-place mutation visible to the caller (quirk 6)
+      } else {
+        const float dv = fmaxf(rintf(expf(logd[s0 + t]) - 1.0f), 0.0f);
+        dl = (alpha != 1.0f) ? static_cast<int>(rintf(dv * alpha)) : static_cast<int>(dv);
+      }
+    }
+    int incl = dl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (t < T) cum[s0 + t] = carry + incl;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) n_frames[b] = carry;
+}
+int durations_and_scan(const float* logd, float alpha, RowLayout L, const int* tok_off, long long* dur_out, int* cum,
+                       int* n_frames, cudaStream_t s) {
+  if (L.nseg == 0) return 0;
+  durations_kernel<<<L.nseg, 32, 0, s>>>(logd, alpha, L, tok_off, dur_out, cum, n_frames);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+__global__ void gather_scalar_kernel(const float* __restrict__ in, RowLayout L, const int* __restrict__ tok_off,
+                                     float* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= L.n_rows) return;
+  const int b = L.frame_seg[r];
+  if (b < 0) return;
+  out[tok_off[b] + (r - L.seg_start[b])] = in[r];
+}
+int gather_scalar(const float* in, RowLayout L, const int* tok_off, float* out, cudaStream_t s) {
+  if (L.n_rows == 0) return 0;
+  gather_scalar_kernel<<<ceil_div(L.n_rows, 256), 256, 0, s>>>(in, L, tok_off, out);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LengthRegulator: prefix-sum gather (one warp per output frame row)
+// ------------------------------------------------------------------------------------------------
+__global__ void length_regulate_kernel(const float* __restrict__ hs, const float* __restrict__ pitch,
+                                       const float* __restrict__ energy, const float* __restrict__ wp,
+                                       const float* __restrict__ bp, const float* __restrict__ we,
+                                       const float* __restrict__ be, int d, float scale, RowLayout Lt,
+                                       const int* __restrict__ cum, RowLayout Lf, const int* __restrict__ frame_off,
+                                       float* __restrict__ x_out, int* __restrict__ lr_index) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= Lf.n_rows) return;
+  const int b = Lf.frame_seg[warp];
+  if (b < 0) return;
+  const int f = warp - Lf.seg_start[b];
+  const int t0 = Lt.seg_start[b], T = Lt.seg_len[b];
+  int lo = 0, hi = T - 1;  // first token whose inclusive cumulative duration exceeds f
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cum[t0 + mid] > f) hi = mid; else lo = mid + 1;
+  }
+  const int trow = t0 + lo;
+  if (lane == 0) lr_index[frame_off[b] + f] = lo;
+  const float p = pitch[trow], e = energy[trow];
+  const float4* src = reinterpret_cast<const float4*>(hs + static_cast<long long>(trow) * d);
+  float4* dst = reinterpret_cast<float4*>(x_out + static_cast<long long>(warp) * d);
+  for (int i = lane; i < d / 4; i += 32) {
+    const float4 h = src[i];
+    const float4 a = reinterpret_cast<const float4*>(wp)[i], ab = reinterpret_cast<const float4*>(bp)[i];
+    const float4 c = reinterpret_cast<const float4*>(we)[i], cb = reinterpret_cast<const float4*>(be)[i];
+    float4 o;
+    // fastspeech2.py:616: hs + e_embs + p_embs  (same association order)
+    o.x = ((h.x + (e * c.x + cb.x)) + (p * a.x + ab.x)) * scale;
+    o.y = ((h.y + (e * c.y + cb.y)) + (p * a.y + ab.y)) * scale;
+    o.z = ((h.z + (e * c.z + cb.z)) + (p * a.z + ab.z)) * scale;
+    o.w = ((h.w + (e * c.w + cb.w)) + (p * a.w + ab.w)) * scale;
+    dst[i] = o;
+  }
+}
+int length_regulate(const float* hs, const float* pitch, const float* energy, const float* wp, const float* bp,
+                    const float* we, const float* be, int d, float scale, RowLayout Ltext, const int* cum,
+                    RowLayout Lframe, const int* frame_off, float* x_out, int* lr_index, cudaStream_t s) {
+  JB_REQUIRE(d % 4 == 0, -2, "length_regulate: d % 4");
+  if (Lframe.n_rows == 0) return 0;
+  length_regulate_kernel<<<ceil_div(Lframe.n_rows, 8), 256, 0, s>>>(hs, pitch, energy, wp, bp, we, be, d, scale, Ltext,
+                                                                    cum, Lframe, frame_off, x_out, lr_index);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack / unpack
+// ------------------------------------------------------------------------------------------------
+__global__ void unpack_rows_kernel(const float* __restrict__ in, int in_ld, int c, RowLayout L,
+                                   const int* __restrict__ off, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int b = L.frame_seg[r];
+  if (b < 0) return;
+  const long long orow = off[b] + (r - L.seg_start[b]);
+  for (int i = threadIdx.x; i < c; i += blockDim.x) out[orow * c + i] = in[static_cast<long long>(r) * in_ld + i];
+}
+int unpack_rows(const float* in, int in_ld, int c, RowLayout L, const int* off, float* out, cudaStream_t s) {
+  if (L.n_rows == 0) return 0;
+  unpack_rows_kernel<<<L.n_rows, 96, 0, s>>>(in, in_ld, c, L, off, out);
+  JB_KERNEL_OK();
+  return 0;
+}
+__global__ void pack_mel_affine_kernel(const float* __restrict__ mel, int c, const float* __restrict__ a,
+                                       const float* __restrict__ bb, RowLayout L, const int* __restrict__ off,
+                                       bf16* __restrict__ out, int out_ld) {
+  const int r = blockIdx.x;
+  const int b = L.frame_seg[r];
+  if (b < 0) return;
+  const long long irow = off[b] + (r - L.seg_start[b]);
+  for (int i = threadIdx.x; i < c; i += blockDim.x)
+    out[static_cast<long long>(r) * out_ld + i] = __float2bfloat16_rn(mel[irow * c + i] * a[i] + bb[i]);
+}
+int pack_mel_affine(const float* mel, int c, const float* a, const float* b, RowLayout L, const int* off, bf16* out,
+                    int out_ld, cudaStream_t s) {
+  if (L.n_rows == 0) return 0;
+  pack_mel_affine_kernel<<<L.n_rows, 96, 0, s>>>(mel, c, a, b, L, off, out, out_ld);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// HiFi-GAN output_conv (C -> 1, k taps) + tanh; one thread per output sample
+// ------------------------------------------------------------------------------------------------
+__global__ void output_conv_tanh_kernel(const bf16* __restrict__ x, int ld, int c, const float* __restrict__ w,
+                                        float bias, int k, RowLayout L, int rate, const int* __restrict__ frame_off,
+                                        float* __restrict__ wave, long long total_rows) {
+  extern __shared__ float ws[];  // [k][c]
+  for (int i = threadIdx.x; i < k * c; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= total_rows) return;
+  const int fr = static_cast<int>(row / rate);
+  const int b = L.frame_seg[fr];
+  if (b < 0) return;
+  const int pad = (k - 1) / 2;
+  float acc = bias;
+  for (int j = 0; j < k; ++j) {
+    const long long rr = row + j - pad;  // gap rows are zero, so no per-tap boundary test is needed
+    if (rr < 0 || rr >= total_rows) continue;
+    const uint4* px = reinterpret_cast<const uint4*>(x + rr * ld);
+    for (int c8 = 0; c8 < c / 8; ++c8) {
+      const uint4 u = px[c8];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        acc += f.x * ws[j * c + c8 * 8 + 2 * q] + f.y * ws[j * c + c8 * 8 + 2 * q + 1];
+      }
+    }
+  }
+  const long long t = row - static_cast<long long>(L.seg_start[b]) * rate;
+  wave[static_cast<long long>(frame_off[b]) * rate + t] = tanhf(acc);
+}
+int output_conv_tanh(const bf16* x, int ld, int c, const float* w, float bias, int k, RowLayout L, int rate,
+                     const int* frame_off, float* wave, cudaStream_t s) {
+  JB_REQUIRE(c % 8 == 0 && ld % 8 == 0, -2, "output_conv: C % 8");
+  const long long total = static_cast<long long>(L.n_rows) * rate;
+  if (total == 0) return 0;
+  output_conv_tanh_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, sizeof(float) * k * c, s>>>(
+      x, ld, c, w, bias, k, L, rate, frame_off, wave, total);
+  JB_KERNEL_OK();
+  return 0;
+}
+
+}  // namespace jb
