@@ -43,10 +43,10 @@ enum {
   JATTS_E_STATE = -4        /* call order violated (run before plan, ...) */
 };
 
-enum { JATTS_F32 = 0, JATTS_BF16 = 1, JATTS_I64 = 2, JATTS_I32 = 3 };
+enum { JATTS_F32 = 0, JATTS_BF16 = 1, JATTS_I64 = 2, JATTS_I32 = 3, JATTS_F16 = 4 };
 
 /* a named, already-repacked weight tensor in device memory (the Python host side does the repacking:
- * BatchNorm folding, tap-major layout, bf16 hi/lo split, channel padding) */
+ * BatchNorm folding, tap-major layout, fp16 (hi, lo*2^11) split pairs, channel padding) */
 typedef struct {
   const char* name;
   const void* d_ptr;
@@ -114,7 +114,7 @@ JATTS_API int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int3
 
 /* ---- op-level entry points used by the parity tests (tests/test_ops_gpu.py) ------------------------ */
 typedef struct {
-  const void* d_a_hi; const void* d_a_lo;     /* bf16 [a_rows, a_ld]; a_lo NULL = single bf16 */
+  const void* d_a_hi; const void* d_a_lo;     /* [a_rows, a_ld]; bf16 if a_lo NULL, else fp16 (hi, lo*2^11) pair */
   int32_t a_rows, a_ld, a_cols;                 /* a_cols: real channels (<= k_pad), 0 = k_pad */
   const void* d_w_hi; const void* d_w_lo;     /* bf16 [taps*n_pad, k_pad] */
   int32_t taps, n_pad, k_pad, tap_off0, tap_stride;

@@ -10,9 +10,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libjatts_b200.so")
+# JATTS_B200_LIB overrides the location (used to A/B kernel build variants on the GPU box)
+LIB_PATH = os.environ.get("JATTS_B200_LIB") or os.path.join(_HERE, "lib", "libjatts_b200.so")
 
-JATTS_F32, JATTS_BF16, JATTS_I64, JATTS_I32 = 0, 1, 2, 3
+JATTS_F32, JATTS_BF16, JATTS_I64, JATTS_I32, JATTS_F16 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_GLU = 0, 1, 2, 3, 4
 
 
@@ -113,7 +114,8 @@ def tensor_table(named):
 
     global _DT
     if _DT is None:
-        _DT = {torch.float32: JATTS_F32, torch.bfloat16: JATTS_BF16, torch.int64: JATTS_I64, torch.int32: JATTS_I32}
+        _DT = {torch.float32: JATTS_F32, torch.bfloat16: JATTS_BF16, torch.int64: JATTS_I64, torch.int32: JATTS_I32,
+               torch.float16: JATTS_F16}
     arr = (Tensor * len(named))()
     keep = []
     for i, (k, t) in enumerate(named.items()):

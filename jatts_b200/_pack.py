@@ -1,7 +1,7 @@
 """Weight repacking for the CUDA engines (host side, done once at load).
 
 Reference-format tensors -> the layouts the kernels consume: tap-major [taps][N_pad][K_pad] bf16
-(hi/lo split pairs for the fp32-faithful text2mel GEMMs), BatchNorm folded into the preceding
+(fp16 hi / scaled-lo split pairs for the fp32-faithful text2mel GEMMs), BatchNorm folded into the preceding
 convolution, GLU halves interleaved per 128-wide tile, ConvTranspose1d split into its two polyphase
 taps, relative-position tables pre-multiplied by ``linear_pos``.
 """
@@ -29,21 +29,26 @@ def pick_block_n(n_cols: int, split: bool) -> int:
     return 32
 
 
-def split_bf16(w: torch.Tensor):
-    hi = w.to(torch.bfloat16)
-    lo = (w - hi.float()).to(torch.bfloat16)
+SPLIT_SCALE = 2048.0  # csrc/common.cuh::kSplitScale
+
+
+def split16(w: torch.Tensor):
+    """fp32 -> fp16 pair (hi, lo) with w ~= hi + lo / 2^11 (22 significand bits); see csrc/common.cuh."""
+    w = w.clamp(-65504.0, 65504.0)
+    hi = w.to(torch.float16)
+    lo = ((w - hi.float()) * SPLIT_SCALE).to(torch.float16)
     return hi, lo
 
 
 def pack_taps(w_tnk: torch.Tensor, split: bool, out: dict, name: str, bias=None):
-    """w_tnk: fp32 [taps, N, K] -> name.hi (/.lo) as [taps, N_pad, K_pad] bf16 (+ name.b)."""
+    """w_tnk: fp32 [taps, N, K] -> name.hi (/.lo) as [taps, N_pad, K_pad] (bf16, or fp16 pair) (+ name.b)."""
     taps, n, k = w_tnk.shape
     bn = pick_block_n(n, split)
     n_pad, k_pad = round_up(n, bn), round_up(k, 64)
     buf = torch.zeros(taps, n_pad, k_pad, dtype=torch.float32)
     buf[:, :n, :k] = w_tnk
     if split:
-        hi, lo = split_bf16(buf)
+        hi, lo = split16(buf)
         out[name + ".hi"], out[name + ".lo"] = hi.contiguous(), lo.contiguous()
     else:
         out[name + ".hi"] = buf.to(torch.bfloat16).contiguous()

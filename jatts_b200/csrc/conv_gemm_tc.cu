@@ -11,8 +11,11 @@
 // K loop = taps x (C_in_pad / 64).  Per K block the producer loads a [128 rows, 64 ch] slab of the
 // activation matrix at row coordinate m0 + tap_off0 + tap*tap_stride (negative / past-the-end rows
 // are zero-filled by TMA) and a [BLOCK_N, 64] slab of the tap's weight matrix.  In SPLIT mode each
-// operand is a bf16 hi/lo pair and every K step issues hi*hi + lo*hi + hi*lo into the same fp32
-// TMEM accumulator (lo*lo is 2^-18 relative and dropped).
+// operand is an fp16 pair x ~= hi + lo*2^-11 (common.cuh::split_op16) and every K step issues
+// hi*hi into the main TMEM accumulator and lo*hi + hi*lo into a correction accumulator that the
+// epilogue rescales by 2^-11 (lo*lo is 2^-24 relative and dropped): fp32-faithful products on the
+// 16-bit tensor-core path.  SPLIT accumulation runs in short chains that the epilogue warps add up
+// in registers, because tcgen05 truncates (not rounds) when it adds into TMEM.
 #include <mutex>
 
 #include "conv_gemm.cuh"
@@ -123,16 +126,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
-// cute::UMMA::InstrDescriptor for kind::f16: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1),
+// cute::UMMA::InstrDescriptor for kind::f16: D=F32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12: 0 = F16, 1 = BF16),
 // both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool is_bf16) {
+  return (1u << 4) | ((is_bf16 ? 1u : 0u) << 7) | ((is_bf16 ? 1u : 0u) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
+#ifndef JB_SPLIT_CHUNK
+#define JB_SPLIT_CHUNK 8
+#endif
 static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
 static constexpr int UMMA_K = 16;
@@ -158,7 +164,12 @@ struct Cfg {
   static constexpr int MAX_STAGES = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // accumulator buffer = [main | correction] in SPLIT mode; two buffers (MMA <-> epilogue ping-pong)
+  static constexpr int ACC_COLS = SPLIT ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  // K blocks per tensor-core accumulation chain; 0 = one chain over all of K.  The fp32-faithful
+  // (SPLIT) GEMMs keep chains short and add the partial sums on CUDA cores (see the epilogue).
+  static constexpr int CHUNK = SPLIT ? JB_SPLIT_CHUNK : 0;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -176,7 +187,7 @@ __device__ __forceinline__ void store_row_segment(const ConvGemmEpilogue& ep, fl
   const bool full = (col + NV <= n_limit);
   if (ep.res_f32) {
     const float* r = ep.res_f32 + orow * ep.res_ld + col;
-    if (full && (ep.res_ld & 3) == 0) {
+    if (NV % 4 == 0 && full && (ep.res_ld & 3) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) {
         float4 t = *reinterpret_cast<const float4*>(r + i);
@@ -190,7 +201,7 @@ __device__ __forceinline__ void store_row_segment(const ConvGemmEpilogue& ep, fl
   }
   if (ep.res_bf16) {
     const bf16* r = ep.res_bf16 + orow * ep.res_ld + col;
-    if (full && (ep.res_ld & 7) == 0) {
+    if (NV % 8 == 0 && full && (ep.res_ld & 7) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 8) {
         uint4 t = *reinterpret_cast<const uint4*>(r + i);
@@ -209,7 +220,7 @@ __device__ __forceinline__ void store_row_segment(const ConvGemmEpilogue& ep, fl
   }
   if (ep.accum_in) {
     const float* r = ep.accum_in + orow * ep.out_f32_ld + col;
-    if (full && (ep.out_f32_ld & 3) == 0) {
+    if (NV % 4 == 0 && full && (ep.out_f32_ld & 3) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) {
         float4 t = *reinterpret_cast<const float4*>(r + i);
@@ -227,7 +238,7 @@ __device__ __forceinline__ void store_row_segment(const ConvGemmEpilogue& ep, fl
   }
   if (ep.out_f32) {
     float* o = ep.out_f32 + orow * ep.out_f32_ld + col;
-    if (full && (ep.out_f32_ld & 3) == 0) {
+    if (NV % 4 == 0 && full && (ep.out_f32_ld & 3) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     } else {
@@ -237,19 +248,28 @@ __device__ __forceinline__ void store_row_segment(const ConvGemmEpilogue& ep, fl
     }
   }
   if (ep.out_hi) {
+    // out_lo given: fp16 split operand pair (common.cuh::split_op16); otherwise a single bf16 copy
     bf16* oh = ep.out_hi + orow * ep.out_bf_ld + col;
     bf16* ol = ep.out_lo ? ep.out_lo + orow * ep.out_bf_ld + col : nullptr;
-    if (full && (ep.out_bf_ld & 7) == 0) {
+    if (NV % 8 == 0 && full && (ep.out_bf_ld & 7) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 8) {
         uint32_t ph[4], pl[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float a = v[i + 2 * j], b = v[i + 2 * j + 1];
-          bf16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+          const float a = v[i + 2 * j], b = v[i + 2 * j + 1];
+          bf16 ah, bh, al, bl;
+          if (ol) {
+            split_op16(a, ah, al);
+            split_op16(b, bh, bl);
+            __nv_bfloat162 ll = __halves2bfloat162(al, bl);
+            pl[j] = *reinterpret_cast<uint32_t*>(&ll);
+          } else {
+            ah = __float2bfloat16_rn(a);
+            bh = __float2bfloat16_rn(b);
+          }
           __nv_bfloat162 hh = __halves2bfloat162(ah, bh);
           ph[j] = *reinterpret_cast<uint32_t*>(&hh);
-          pl[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
         }
         *reinterpret_cast<uint4*>(oh + i) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
         if (ol) *reinterpret_cast<uint4*>(ol + i) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -258,16 +278,21 @@ __device__ __forceinline__ void store_row_segment(const ConvGemmEpilogue& ep, fl
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         if (col + i < n_limit) {
-          bf16 h = __float2bfloat16_rn(v[i]);
-          oh[i] = h;
-          if (ol) ol[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+          if (ol) {
+            bf16 h, l;
+            split_op16(v[i], h, l);
+            oh[i] = h;
+            ol[i] = l;
+          } else {
+            oh[i] = __float2bfloat16_rn(v[i]);
+          }
         }
     }
   }
   if (ep.out_act) {
     bf16* oa = ep.out_act + orow * ep.out_act_ld + col;
     const float s = ep.out_act_slope;
-    if (full && (ep.out_act_ld & 7) == 0) {
+    if (NV % 8 == 0 && full && (ep.out_act_ld & 7) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 8) {
         uint32_t pa[4];
@@ -367,37 +392,44 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, /*is_bf16=*/!SPLIT);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+        int it = 0;
+        while (it < k_iters) {
+          // one accumulation chain = CHUNK K blocks (all of K when CHUNK == 0); see Cfg::CHUNK
+          const int it_begin = it;
+          const int it_end = (C::CHUNK > 0 && it + C::CHUNK < k_iters) ? it + C::CHUNK : k_iters;
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint64_t da_hi = make_sw128_desc(sa);
-          const uint64_t db_hi = make_sw128_desc(sa + C::A_BYTES);
-          const uint64_t da_lo = make_sw128_desc(sa + C::A_BYTES + C::B_BYTES);
-          const uint64_t db_lo = make_sw128_desc(sa + 2 * C::A_BYTES + C::B_BYTES);
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * C::ACC_COLS);
+          const uint32_t tmem_c = tmem_d + BLOCK_N;  // SPLIT: lo*hi + hi*lo products (scaled by 2^11)
+          for (; it < it_end; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint64_t da_hi = make_sw128_desc(sa);
+            const uint64_t db_hi = make_sw128_desc(sa + C::A_BYTES);
+            const uint64_t da_lo = make_sw128_desc(sa + C::A_BYTES + C::B_BYTES);
+            const uint64_t db_lo = make_sw128_desc(sa + 2 * C::A_BYTES + C::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
-            tc_mma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (it | k) != 0 ? 1u : 0u);
-            if (SPLIT) {
-              tc_mma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
-              tc_mma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);  // +32 B per K step
+              tc_mma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (it != it_begin || k != 0) ? 1u : 0u);
+              if (SPLIT) {
+                tc_mma_bf16(tmem_c, da_lo + koff, db_hi + koff, idesc, (it != it_begin || k != 0) ? 1u : 0u);
+                tc_mma_bf16(tmem_c, da_hi + koff, db_lo + koff, idesc, 1u);
+              }
             }
+            tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tc_commit(&tfull_bar[acc]);      // chain complete -> epilogue warps
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -406,44 +438,79 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     const ConvGemmEpilogue& ep = P.ep;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int n_chains = C::CHUNK > 0 ? (k_iters + C::CHUNK - 1) / C::CHUNK : 1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / P.num_n_tiles) * BLOCK_M;
       const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
       const int row = m0 + lane_group * 32 + lane;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) +
-                             static_cast<uint32_t>(acc * BLOCK_N);
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
+      // Chained mode: sum the partial accumulators in registers with round-to-nearest fp32 adds.
+      // (tcgen05 truncates when it adds into the TMEM accumulator; measured bias 1.7e-5 relative
+      // after 288 MMAs -- too much for the 1e-3 mel budget, so chains are kept short.)
+      float accr[C::CHUNK > 0 ? BLOCK_N : 1];
+      if (C::CHUNK > 0) {
+        for (int ch = 0; ch < n_chains; ++ch) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t r[32], rc[32];
+            tmem_ld32(lane_addr + static_cast<uint32_t>(acc * C::ACC_COLS + c), r);
+            tmem_ld32(lane_addr + static_cast<uint32_t>(acc * C::ACC_COLS + BLOCK_N + c), rc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = fmaf(__uint_as_float(rc[i]), 1.0f / kSplitScale, __uint_as_float(r[i]));
+              const int idx = C::CHUNK > 0 ? c + i : 0;
+              accr[idx] = (ch == 0) ? x : accr[idx] + x;
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+      }
+      const uint32_t taddr = lane_addr + static_cast<uint32_t>(acc * C::ACC_COLS);
       if (ep.act == ACT_GLU) {
         // tile columns [0, BLOCK_N/2) hold the linear half, [BLOCK_N/2, BLOCK_N) the gate half of the
         // same BLOCK_N/2 output channels (weights are interleaved per tile on the host).
         constexpr int HALF = BLOCK_N / 2;
         bool valid = row < P.m_rows;
         if (valid && P.frame_mask) valid = P.frame_mask[row / P.rate] != 0;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < HALF; c += 32) {
           uint32_t ra[32], rb[32];
-          tmem_ld32(taddr + c, ra);
-          tmem_ld32(taddr + HALF + c, rb);
-          tmem_ld_wait();
+          if (C::CHUNK == 0) {
+            tmem_ld32(taddr + c, ra);
+            tmem_ld32(taddr + HALF + c, rb);
+            tmem_ld_wait();
+          }
           if (valid) {
             float v[32];
             const int ocol = n0 / 2 + c;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float a = __uint_as_float(ra[i]) + (ep.bias ? __ldg(ep.bias + n0 + c + i) : 0.f);
-              float g = __uint_as_float(rb[i]) + (ep.bias ? __ldg(ep.bias + n0 + HALF + c + i) : 0.f);
+              const float xa = C::CHUNK > 0 ? accr[(C::CHUNK > 0 ? c + i : 0)] : __uint_as_float(ra[i]);
+              const float xg = C::CHUNK > 0 ? accr[(C::CHUNK > 0 ? HALF + c + i : 0)] : __uint_as_float(rb[i]);
+              float a = xa + (ep.bias ? __ldg(ep.bias + n0 + c + i) : 0.f);
+              float g = xg + (ep.bias ? __ldg(ep.bias + n0 + HALF + c + i) : 0.f);
               v[i] = a * (1.0f / (1.0f + __expf(-g))) * ep.scale;
             }
             store_row_segment<32>(ep, v, row, ocol, P.n);
           }
         }
       } else {
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < BLOCK_N; c += 32) {
           uint32_t r[32];
-          tmem_ld32(taddr + c, r);
-          tmem_ld_wait();
+          if (C::CHUNK == 0) {
+            tmem_ld32(taddr + c, r);
+            tmem_ld_wait();
+          }
           const int ncol = n0 + c;  // column in GEMM-N space
           long long orow = row;
           int ocol = ncol;
@@ -460,7 +527,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float x = __uint_as_float(r[i]);
+              float x = C::CHUNK > 0 ? accr[(C::CHUNK > 0 ? c + i : 0)] : __uint_as_float(r[i]);
               if (ep.bias) x += __ldg(ep.bias + (P.up_s > 0 ? ocol + i : ncol + i < P.n ? ncol + i : 0));
               v[i] = apply_act(x, ep.act, ep.slope) * ep.scale;
             }
@@ -468,10 +535,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (C::CHUNK == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   }
 
@@ -608,7 +677,9 @@ int conv_gemm_tc(const ConvGemmProblem& p, cudaStream_t stream) {
     case 32: return split ? launch<32, true>(p, stream) : launch<32, false>(p, stream);
     case 64: return split ? launch<64, true>(p, stream) : launch<64, false>(p, stream);
     case 128: return split ? launch<128, true>(p, stream) : launch<128, false>(p, stream);
-    case 256: return split ? launch<256, true>(p, stream) : launch<256, false>(p, stream);
+    case 256:
+      JB_REQUIRE(!split, -2, "conv_gemm: split mode supports block_n <= 128");
+      return launch<256, false>(p, stream);
   }
   return -2;
 }
@@ -632,10 +703,18 @@ __global__ void conv_gemm_simt_kernel(const bf16* __restrict__ a_hi, const bf16*
       const bf16* ah = a_hi + ar * a_ld;
       const bf16* al = a_lo ? a_lo + ar * a_ld : nullptr;
       const long long wr = (static_cast<long long>(tap) * P.n_pad + wcol) * k_pad;
-      for (int c = 0; c < a_cols; ++c) {
-        float x = __bfloat162float(ah[c]), w = __bfloat162float(w_hi[wr + c]);
-        acc += x * w;
-        if (al) acc += __bfloat162float(al[c]) * w + x * __bfloat162float(w_lo[wr + c]);
+      if (al) {  // fp16 split pairs: x = hi + lo * 2^-11 (common.cuh::split_op16)
+        const __half* xh = reinterpret_cast<const __half*>(ah);
+        const __half* xl = reinterpret_cast<const __half*>(al);
+        const __half* wh = reinterpret_cast<const __half*>(w_hi) + wr;
+        const __half* wl = reinterpret_cast<const __half*>(w_lo) + wr;
+        for (int c = 0; c < a_cols; ++c) {
+          const float x = __half2float(xh[c]) + __half2float(xl[c]) * (1.0f / kSplitScale);
+          const float w = __half2float(wh[c]) + __half2float(wl[c]) * (1.0f / kSplitScale);
+          acc += x * w;
+        }
+      } else {
+        for (int c = 0; c < a_cols; ++c) acc += __bfloat162float(ah[c]) * __bfloat162float(w_hi[wr + c]);
       }
     }
     return acc;

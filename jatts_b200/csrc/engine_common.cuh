@@ -36,7 +36,7 @@ struct WeightTable {
   }
 };
 
-// One convolution's repacked weights: [taps][n_pad][k_pad] bf16 (+ lo part in split mode).
+// One convolution's repacked weights: [taps][n_pad][k_pad] bf16, or an fp16 (hi, lo*2^11) pair in split mode.
 struct ConvW {
   const bf16* hi = nullptr;
   const bf16* lo = nullptr;
@@ -61,8 +61,9 @@ inline int load_conv(const WeightTable& wt, const std::string& name, int taps, i
   w->n_pad = round_up(n_cols, w->block_n);
   w->k_pad = round_up(c_in, 64);
   const long long numel = static_cast<long long>(taps) * w->n_pad * w->k_pad;
-  JB_PROPAGATE(wt.get(name + ".hi", JATTS_BF16, numel, reinterpret_cast<const void**>(&w->hi)));
-  if (split) JB_PROPAGATE(wt.get(name + ".lo", JATTS_BF16, numel, reinterpret_cast<const void**>(&w->lo)));
+  // split weights are fp16 pairs (hi, lo * 2^11), plain weights bf16
+  JB_PROPAGATE(wt.get(name + ".hi", split ? JATTS_F16 : JATTS_BF16, numel, reinterpret_cast<const void**>(&w->hi)));
+  if (split) JB_PROPAGATE(wt.get(name + ".lo", JATTS_F16, numel, reinterpret_cast<const void**>(&w->lo)));
   if (has_bias) JB_PROPAGATE(wt.f32(name + ".b", -1, &w->bias));
   return 0;
 }

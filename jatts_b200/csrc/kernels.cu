@@ -127,7 +127,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int c, const float
         if (y) reinterpret_cast<float4*>(y + r * c)[j] = o;
         if (hi) {
           bf16 h0, h1, h2, h3, l0, l1, l2, l3;
-          split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
+          split_op16(o.x, h0, l0); split_op16(o.y, h1, l1); split_op16(o.z, h2, l2); split_op16(o.w, h3, l3);
           __nv_bfloat162 p0 = __halves2bfloat162(h0, h1), p1 = __halves2bfloat162(h2, h3);
           uint2 ph = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
           reinterpret_cast<uint2*>(hi + r * bf_ld)[j] = ph;
@@ -171,7 +171,7 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int c, RowLayout 
   if (!L.frame_mask[r]) return;
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
     bf16 h, l;
-    split_bf16(x[static_cast<long long>(r) * c + i], h, l);
+    split_op16(x[static_cast<long long>(r) * c + i], h, l);
     hi[static_cast<long long>(r) * bf_ld + i] = h;
     lo[static_cast<long long>(r) * bf_ld + i] = l;
   }
@@ -354,7 +354,7 @@ relpos_attention_kernel(const float* __restrict__ qkv, const float* __restrict__
       const int d = tx + 64 * j;
       if (d < dk) {
         bf16 hh, ll;
-        split_bf16(ctx[i][j], hh, ll);
+        split_op16(ctx[i][j], hh, ll);
         out_hi[(base + a) * out_ld + h * dk + d] = hh;
         if (out_lo) out_lo[(base + a) * out_ld + h * dk + d] = ll;
       }
@@ -413,7 +413,7 @@ __global__ void dwconv_swish_kernel(const float* __restrict__ g, int c, const fl
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float y = o[i] * (1.0f / (1.0f + expf(-o[i])));  // swish.py:13-18
-      split_bf16(y, hh[i], ll[i]);
+      split_op16(y, hh[i], ll[i]);
     }
     __nv_bfloat162 p0 = __halves2bfloat162(hh[0], hh[1]), p1 = __halves2bfloat162(hh[2], hh[3]);
     reinterpret_cast<uint2*>(out_hi + static_cast<long long>(r) * out_ld)[c4] =

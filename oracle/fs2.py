@@ -129,7 +129,7 @@ def conformer_stack(x, sd, prefix, n_layers, n_head):
     (positional_encoding.py:221-235; also applied to the decoder input, encoder.py:138-141),
     N layers, after_norm."""
     t, d = x.shape
-    pos_emb = legacy_rel_pe_table(d, t)
+    pos_emb = legacy_rel_pe_table(d, t, x.dtype)
     x = x * math.sqrt(d)
     for i in range(n_layers):
         x = conformer_layer(x, pos_emb, sd, f"{prefix}.encoders.{i}.", n_head)

@@ -61,7 +61,7 @@ HIFIGAN_V1_CANONICAL = dict(
     HIFIGAN_V1_HOP300, upsample_scales=(8, 8, 2, 2), upsample_kernel_sizes=(16, 16, 4, 4)
 )
 HIFIGAN_TINY = dict(
-    HIFIGAN_V1_HOP300, channels=64, upsample_scales=(3, 2), upsample_kernel_sizes=(6, 4),
+    HIFIGAN_V1_HOP300, channels=128, upsample_scales=(3, 2), upsample_kernel_sizes=(6, 4),
     resblock_kernel_sizes=(3, 7), resblock_dilations=((1, 3), (1, 3)),
 )
 SAMPLING_RATE = 24000
@@ -166,7 +166,8 @@ def make_fs2_state_dict(cfg: dict, seed: int = 0, stress: bool = True,
 
     duration_recipe "A": ``duration_predictor.linear.weight *= 0.1; bias = log 7`` (durations ~5-8,
     50 phonemes -> ~300 frames: the throughput workload).  "B": weight unscaled, ``bias = log 3``
-    (wide spread including zeros: the parity stress case).  SURVEY.md 8(d).
+    (wide spread including zeros: the parity stress case).  "Z": all durations predicted 0 (the
+    regulator's all-zero fallback).  SURVEY.md 8(d).
     """
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for name, shape in fs2_state_shapes(cfg).items():
@@ -199,6 +200,9 @@ def make_fs2_state_dict(cfg: dict, seed: int = 0, stress: bool = True,
         sd["duration_predictor.linear.bias"] = torch.full((1,), math.log(7.0))
     elif duration_recipe == "B":
         sd["duration_predictor.linear.bias"] = torch.full((1,), math.log(3.0))
+    elif duration_recipe == "Z":  # every predicted duration rounds to 0: length_regulator.py:86-94 fallback
+        sd["duration_predictor.linear.weight"] = sd["duration_predictor.linear.weight"] * 0.1
+        sd["duration_predictor.linear.bias"] = torch.full((1,), -3.0)
     else:
         raise ValueError(duration_recipe)
     return sd

@@ -8,8 +8,9 @@ from jatts_b200._pack import round_up
 
 
 def split(x):
-    hi = x.to(torch.bfloat16)
-    lo = (x - hi.float()).to(torch.bfloat16)
+    """fp16 (hi, lo*2^11) operand pair, jatts_b200/_pack.py::split16"""
+    hi = x.to(torch.float16)
+    lo = ((x - hi.float()) * 2048.0).to(torch.float16)
     return hi, lo
 
 
@@ -37,8 +38,8 @@ class Case:
         if split_mode:
             self.a_hi, self.a_lo = split(a)
             self.w_hi, self.w_lo = split(w)
-            self.a_eff = self.a_hi.double() + self.a_lo.double()
-            self.w_eff = self.w_hi.double() + self.w_lo.double()
+            self.a_eff = self.a_hi.double() + self.a_lo.double() / 2048.0
+            self.w_eff = self.w_hi.double() + self.w_lo.double() / 2048.0
         else:
             self.a_hi, self.a_lo = a.to(torch.bfloat16), None
             self.w_hi, self.w_lo = w.to(torch.bfloat16), None
@@ -58,7 +59,7 @@ class Case:
         elif res == "bf16":
             self.res_t = torch.randn(self.out_rows, self.out_cols, generator=g).to(torch.bfloat16)
         self.acc_t = torch.randn(self.out_rows, self.out_cols, generator=g) if accum else None
-        self.sentinel = 777.0
+        self.sentinel = 768.0  # exactly representable in bf16 / fp16
 
     # ---- fp64 reference --------------------------------------------------------------------------
     def reference(self):
@@ -89,7 +90,10 @@ class Case:
                 rows = torch.arange(m) * s + q - p
                 ok = (rows >= 0) & (rows < self.out_rows)
                 out[rows[ok]] = acc[ok][:, q * co:(q + 1) * co]
-            assert not torch.isnan(out).any()
+            # the last p output rows need input row m (the zero gap row in the engine's layout), which
+            # this stand-alone problem does not have: they are simply not produced
+            self._uncovered = torch.isnan(out).any(1)
+            out = torch.nan_to_num(out)
             if self.bias is not None:
                 out = out + self.bias.double()
             out = self._act(out) * self.scale
@@ -104,8 +108,10 @@ class Case:
             out = out + self.acc_t.double()
         out = out * self.post_scale
         valid = torch.ones(self.out_rows, dtype=torch.bool)
+        if self.up_s:
+            valid &= ~self._uncovered
         if self.mask is not None:
-            valid = self.mask[torch.arange(self.out_rows) // self.rate].bool()
+            valid &= self.mask[torch.arange(self.out_rows) // self.rate].bool()
         return out, valid
 
     def _act(self, x):
@@ -122,14 +128,14 @@ class Case:
         def pad_a(t):
             if t is None:
                 return None
-            buf = torch.zeros(self.m, self.a_ld, dtype=torch.bfloat16)
+            buf = torch.zeros(self.m, self.a_ld, dtype=t.dtype)
             buf[:, :self.c_in] = t
             return buf.to(dev)
 
         def pad_w(t):
             if t is None:
                 return None
-            buf = torch.zeros(self.taps, self.n_pad, self.k_pad, dtype=torch.bfloat16)
+            buf = torch.zeros(self.taps, self.n_pad, self.k_pad, dtype=t.dtype)
             buf[:, :self.n_cols, :self.c_in] = t
             return buf.to(dev)
 
@@ -164,10 +170,11 @@ class Case:
             args.d_out_f32 = outs["f32"].data_ptr()
         args.out_f32_ld = ld
         if "hi" in self.out:
-            outs["hi"] = torch.full((self.out_rows, ld), self.sentinel, device=dev, dtype=torch.bfloat16)
+            outs["hi"] = torch.full((self.out_rows, ld), self.sentinel, device=dev,
+                                    dtype=torch.float16 if "lo" in self.out else torch.bfloat16)
             args.d_out_hi = outs["hi"].data_ptr()
         if "lo" in self.out:
-            outs["lo"] = torch.full((self.out_rows, ld), self.sentinel, device=dev, dtype=torch.bfloat16)
+            outs["lo"] = torch.full((self.out_rows, ld), self.sentinel, device=dev, dtype=torch.float16)
             args.d_out_lo = outs["lo"].data_ptr()
         args.out_bf_ld = ld
         if "act" in self.out:
@@ -191,7 +198,7 @@ class Case:
             elif k == "hi":
                 res[k] = float((vd[valid] - ref[valid]).abs().max() / max(1.0, float(ref[valid].abs().max())))
             elif k == "lo":
-                tot = outs["hi"].double() + vd
+                tot = outs["hi"].double() + vd / 2048.0
                 res["hi+lo"] = float((tot[valid] - ref[valid]).abs().max())
             elif k == "act":
                 r = torch.where(ref > 0, ref, ref * 0.1)

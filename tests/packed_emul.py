@@ -1,0 +1,168 @@
+"""CPU emulation of the CUDA engines' dataflow FROM THE PACKED WEIGHT TABLES (test helper).
+
+Lets the `-m "not gpu"` suite verify the host-side repacking (BatchNorm folding, GLU interleave,
+tap-major layout, polyphase transposed conv, precomputed positional tables, closed-form rel-shift)
+against the oracle without a GPU.  Never imported by the product.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from jatts_b200._pack import pick_block_n, round_up
+
+
+def W(p, name, n, k):
+    """[taps, n_pad, k_pad] hi(+lo) -> fp32 [taps, n, k]"""
+    w = p[name + ".hi"].float()
+    if name + ".lo" in p:
+        w = w + p[name + ".lo"].float() / 2048.0
+    return w[:, :n, :k]
+
+
+def conv(p, name, x, n, dil=1):
+    """x: [T, C_in] -> [T, n] 'same' conv from the packed taps"""
+    k = x.shape[1]
+    w = W(p, name, n, k)
+    taps = w.shape[0]
+    pad = (taps - 1) // 2 * dil
+    xp = F.pad(x, (0, 0, pad, pad))
+    out = torch.zeros(x.shape[0], n)
+    for j in range(taps):
+        out += xp[j * dil:j * dil + x.shape[0]] @ w[j].t()
+    if name + ".b" in p:
+        out = out + p[name + ".b"][:n]
+    return out
+
+
+def ln(p, name, x):
+    return F.layer_norm(x, (x.shape[-1],), p[name + ".g"], p[name + ".b"], 1e-12)
+
+
+def rel_attention(p, pre, qkv, n_head):
+    t, d3 = qkv.shape
+    d = d3 // 3
+    dk = d // n_head
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    pos = p[pre + "pos"][:t]
+    out = torch.zeros(t, d)
+    for h in range(n_head):
+        sl = slice(h * dk, (h + 1) * dk)
+        qu = q[:, sl] + p[pre + "bias_u"][sl]
+        qv = q[:, sl] + p[pre + "bias_v"][sl]
+        ac = qu @ k[:, sl].t()
+        bd = qv @ pos[:, sl].t()
+        sh = torch.zeros(t, t)
+        for a in range(t):  # closed form of the legacy rel_shift
+            for b in range(t):
+                if b <= a:
+                    sh[a, b] = bd[a, t - 1 - a + b]
+                elif b > a + 1:
+                    sh[a, b] = bd[a + 1, b - a - 2]
+        att = torch.softmax((ac + sh) / math.sqrt(dk), dim=-1)
+        out[:, sl] = att @ v[:, sl]
+    return out
+
+
+def conformer(p, pre, x, n_layers, n_head, units):
+    d = x.shape[1]
+    for i in range(n_layers):
+        q = f"{pre}.{i}."
+        h = ln(p, q + "ln_ffm", x)
+        x = x + 0.5 * conv(p, q + "ffm_w2", torch.relu(conv(p, q + "ffm_w1", h, units)), d)
+        h = ln(p, q + "ln_mha", x)
+        x = x + conv(p, q + "out", rel_attention(p, q, conv(p, q + "qkv", h, 3 * d), n_head), d)
+        h = ln(p, q + "ln_conv", x)
+        g2 = conv(p, q + "pw1", h, 2 * d)  # interleaved [64 a | 64 gate] per 128 tile
+        g2 = g2.view(-1, d // 64, 2, 64)
+        g = (g2[:, :, 0] * torch.sigmoid(g2[:, :, 1])).reshape(-1, d)
+        wT, bb = p[q + "dw.wT"], p[q + "dw.b"]
+        kk = wT.shape[0]
+        gp = F.pad(g, (0, 0, (kk - 1) // 2, (kk - 1) // 2))
+        y = bb.expand(g.shape[0], d).clone()
+        for j in range(kk):
+            y = y + gp[j:j + g.shape[0]] * wT[j]
+        y = y * torch.sigmoid(y)
+        x = x + conv(p, q + "pw2", y, d)
+        h = ln(p, q + "ln_ff", x)
+        x = x + 0.5 * conv(p, q + "ff_w2", torch.relu(conv(p, q + "ff_w1", h, units)), d)
+        x = ln(p, q + "ln_final", x)
+    return ln(p, pre + ".after_norm", x)
+
+
+def predictor(p, pre, hs, n_layers, chans):
+    h = hs
+    for i in range(n_layers):
+        h = ln(p, f"{pre}.ln{i}", torch.relu(conv(p, f"{pre}.conv{i}", h, chans)))
+    return h @ p[pre + ".lin_w"] + p[pre + ".lin_b"]
+
+
+def emul_fs2(p, cfg, text, spemb=None, alpha=1.0):
+    d = cfg["adim"]
+    x = p["emb"][text] * math.sqrt(d)
+    hs = conformer(p, "enc", x, cfg["elayers"], cfg["aheads"], cfg["eunits"])
+    if spemb is not None:
+        hs = hs + (F.normalize(spemb.unsqueeze(0)).squeeze(0) @ p["spk.w"].t() + p["spk.b"])
+    pit = predictor(p, "pitch", hs, cfg["pitch_predictor_layers"], cfg["pitch_predictor_chans"])
+    en = predictor(p, "energy", hs, cfg["energy_predictor_layers"], cfg["energy_predictor_chans"])
+    logd = predictor(p, "dur", hs, cfg["duration_predictor_layers"], cfg["duration_predictor_chans"])
+    dur = torch.clamp(torch.round(logd.exp() - 1.0), min=0).long()
+    dl = dur if alpha == 1.0 else torch.round(dur.float() * alpha).long()
+    dret = dur
+    if int(dl.sum()) == 0:
+        dl = torch.ones_like(dl)
+        if alpha == 1.0:
+            dret = dl
+    cum = torch.cumsum(dl, 0)
+    idx = torch.searchsorted(cum, torch.arange(int(cum[-1])), right=True)
+    hs2 = (hs + (en[:, None] * p["energy_embed.w"] + p["energy_embed.b"])) + (pit[:, None] * p["pitch_embed.w"] + p["pitch_embed.b"])
+    z = conformer(p, "dec", hs2[idx] * math.sqrt(d), cfg["dlayers"], cfg["aheads"], cfg["dunits"])
+    before = conv(p, "feat_out", z, cfg["odim"])
+    h = before
+    nl = cfg["postnet_layers"]
+    for i in range(nl):
+        co = cfg["odim"] if i == nl - 1 else cfg["postnet_chans"]
+        h = conv(p, f"postnet{i}", h, co)
+        if i != nl - 1:
+            h = torch.tanh(h)
+    return dict(feat_gen=before + h, duration=dret, pitch=pit.unsqueeze(-1), energy=en.unsqueeze(-1), lr_index=idx)
+
+
+def emul_hifigan(p, cfg, mel):
+    """mel (T, 80) -> (T*hop,) using the packed taps incl. the polyphase transposed conv"""
+    lrelu = lambda t, s=cfg["slope"]: torch.where(t > 0, t, t * s)
+    x = mel * p["mel_scale"] + p["mel_shift"]
+    x = conv(p, "input_conv", x, cfg["channels"])
+    nb = len(cfg["resblock_kernel_sizes"])
+    for i, s in enumerate(cfg["upsample_scales"]):
+        co = cfg["channels"] >> (i + 1)
+        ci = cfg["channels"] >> i
+        xa = lrelu(x)
+        w = W(p, f"ups{i}", s * co, ci)  # [2, s*co, ci]
+        L = xa.shape[0]
+        xpad = torch.cat([xa, torch.zeros(1, ci)], 0)            # row j = L reads the zero gap row
+        xprev = torch.cat([torch.zeros(1, ci), xa], 0)           # x[j-1]
+        acc = xpad @ w[0].t() + xprev @ w[1].t()                  # [L+1, s*co]
+        pp = s // 2 + s % 2
+        out = torch.zeros(L * s, co)
+        for q in range(s):
+            rows = torch.arange(L + 1) * s + q - pp
+            ok = (rows >= 0) & (rows < L * s)
+            out[rows[ok]] = acc[ok][:, q * co:(q + 1) * co]
+        x0 = out + p[f"ups{i}.b"]
+        total = 0
+        for j in range(nb):
+            xr = x0
+            for d, dil in enumerate(cfg["resblock_dilations"][j]):
+                t = lrelu(conv(p, f"rb{i}_{j}.c1_{d}", lrelu(xr), co, dil))
+                xr = conv(p, f"rb{i}_{j}.c2_{d}", t, co) + xr
+            total = total + xr
+        x = total / nb
+    xa = torch.where(x > 0, x, x * 0.01)
+    wo = p["output.w"]  # [k, C]
+    k = wo.shape[0]
+    xp = F.pad(xa, (0, 0, (k - 1) // 2, (k - 1) // 2))
+    y = p["output.b"].expand(x.shape[0]).clone()
+    for j in range(k):
+        y = y + xp[j:j + x.shape[0]] @ wo[j]
+    return torch.tanh(y)

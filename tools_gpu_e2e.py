@@ -13,8 +13,9 @@ from oracle import recipes
 torch.set_num_threads(16)
 dev = "cuda"
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+import traceback
 
-if which in ("all", "hifigan_tiny", "hifigan"):
+def run_hifigan():
     for cfgname in (["HIFIGAN_TINY"] if which == "hifigan_tiny" else ["HIFIGAN_TINY", "HIFIGAN_V1_HOP300"]):
         cfg = getattr(recipes, cfgname)
         sd = recipes.make_hifigan_state_dict(cfg, 0)
@@ -32,7 +33,7 @@ if which in ("all", "hifigan_tiny", "hifigan"):
             print("  T", m.shape[0], "shape", tuple(yc.shape), tuple(ref.shape), "snr_db %.2f" % ohg.ac_snr_db(ref, yc),
                   "maxabs %.4f" % float((ref - yc).abs().max()), "ref std %.3f" % float(ref.std()), flush=True)
 
-if which in ("all", "fs2_tiny", "fs2"):
+def run_fs2():
     for cfgname, T in ([("TINY_FS2", [13, 7, 20])] if which == "fs2_tiny" else [("TINY_FS2", [13, 7, 20]), ("JSUT_FS2", [50, 31, 50, 5])]):
         cfg = getattr(recipes, cfgname)
         for recipe in ("A", "B"):
@@ -59,4 +60,10 @@ if which in ("all", "fs2_tiny", "fs2"):
                 else:
                     line += f" ref_d {ref['duration'].tolist()} got {o['duration'].cpu().tolist()}"
                 print(line, flush=True)
+for fn, keys in ((run_hifigan, ("all", "hifigan_tiny", "hifigan")), (run_fs2, ("all", "fs2_tiny", "fs2"))):
+    if which in keys:
+        try:
+            fn()
+        except Exception:
+            traceback.print_exc()
 print("done", flush=True)
