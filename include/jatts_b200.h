@@ -62,6 +62,12 @@ JATTS_API const char* jatts_last_error(void);
 /* number of kernels this library has launched since load (all handles); bench.py reports the delta */
 JATTS_API int64_t jatts_launch_count(void);
 
+/* Per-launch device timing of the tcgen05 convolution kernel (CUDA events on the launching stream),
+ * for bench.py's roofline leg.  begin() arms it; end() waits for the recorded launches and returns the
+ * summed duration / launch count of the bf16 (HiFi-GAN) and split-fp16 (FastSpeech2) instantiations. */
+JATTS_API int jatts_profile_begin(void);
+JATTS_API int jatts_profile_end(double* ms_bf16, int64_t* n_bf16, double* ms_split, int64_t* n_split);
+
 /* ---- FastSpeech2 (replaces jatts/models/fastspeech2.py:566-735 on the inference path) ------------ */
 typedef struct {
   int32_t idim, odim, adim, aheads;

@@ -59,6 +59,7 @@ EXPORTS = (
     "jatts_abi_version", "jatts_last_error", "jatts_launch_count",
     "jatts_fs2_create", "jatts_fs2_destroy", "jatts_fs2_plan", "jatts_fs2_run",
     "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_op_conv_gemm",
+    "jatts_profile_begin", "jatts_profile_end",
 )
 
 
@@ -84,6 +85,8 @@ def _load():
     lib.jatts_hifigan_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
                                       C.c_void_p]
     lib.jatts_op_conv_gemm.argtypes = [C.POINTER(ConvGemmArgs), C.c_int32, C.c_void_p]
+    lib.jatts_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_int64)]
     if lib.jatts_abi_version() != 1:
         raise RuntimeError("jatts_b200: ABI version mismatch between the Python host side and the library")
     return lib
@@ -128,3 +131,14 @@ def tensor_table(named):
 
 def launch_count() -> int:
     return int(lib.jatts_launch_count())
+
+
+def profile_begin() -> None:
+    check(lib.jatts_profile_begin(), "profile_begin")
+
+
+def profile_end():
+    """-> dict(ms_bf16, n_bf16, ms_split, n_split): summed device time of the tcgen05 conv launches"""
+    a, b, c, d = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
+    check(lib.jatts_profile_end(C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "profile_end")
+    return dict(ms_bf16=a.value, n_bf16=b.value, ms_split=c.value, n_split=d.value)

@@ -29,3 +29,31 @@ extern "C" int jatts_op_conv_gemm(const jatts_conv_gemm_args* a, int32_t impl, v
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return impl == 0 ? conv_gemm_tc(p, s) : conv_gemm_simt_debug(p, s);
 }
+
+extern "C" int jatts_profile_begin(void) {
+  for (auto& e : g_profile_events) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+  g_profile_events.clear();
+  g_profile_on = true;
+  return 0;
+}
+
+extern "C" int jatts_profile_end(double* ms_bf16, int64_t* n_bf16, double* ms_split, int64_t* n_split) {
+  g_profile_on = false;
+  double ms[2] = {0.0, 0.0};
+  int64_t n[2] = {0, 0};
+  for (auto& e : g_profile_events) {
+    JB_CUDA_OK(cudaEventSynchronize(e.e1));
+    float t = 0.f;
+    JB_CUDA_OK(cudaEventElapsedTime(&t, e.e0, e.e1));
+    ms[e.split] += t;
+    n[e.split] += 1;
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+  g_profile_events.clear();
+  if (ms_bf16) *ms_bf16 = ms[0];
+  if (n_bf16) *n_bf16 = n[0];
+  if (ms_split) *ms_split = ms[1];
+  if (n_split) *n_split = n[1];
+  return 0;
+}

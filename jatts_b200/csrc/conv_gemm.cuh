@@ -8,6 +8,8 @@
 // per-utterance zero padding comes from the packed-with-gaps layout (common.cuh) and from TMA
 // out-of-bounds zero fill at the ends of the buffer.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace jb {
@@ -62,5 +64,10 @@ int conv_gemm_tc(const ConvGemmProblem& p, cudaStream_t stream);
 int conv_gemm_simt_debug(const ConvGemmProblem& p, cudaStream_t stream);
 
 int num_sms();
+
+// optional per-launch device timing of the tcgen05 kernel (jatts_profile_begin / jatts_profile_end)
+struct ProfileEvent { cudaEvent_t e0, e1; int split; };
+extern bool g_profile_on;
+extern std::vector<ProfileEvent> g_profile_events;
 
 }  // namespace jb

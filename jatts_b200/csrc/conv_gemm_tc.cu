@@ -17,6 +17,7 @@
 // 16-bit tensor-core path.  SPLIT accumulation runs in short chains that the epilogue warps add up
 // in registers, because tcgen05 truncates (not rounds) when it adds into TMEM.
 #include <mutex>
+#include <vector>
 
 #include "conv_gemm.cuh"
 
@@ -481,7 +482,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         constexpr int HALF = BLOCK_N / 2;
         bool valid = row < P.m_rows;
         if (valid && P.frame_mask) valid = P.frame_mask[row / P.rate] != 0;
-#pragma unroll
+#pragma unroll(C::CHUNK > 0 ? HALF / 32 : 1)
         for (int c = 0; c < HALF; c += 32) {
           uint32_t ra[32], rb[32];
           if (C::CHUNK == 0) {
@@ -504,7 +505,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           }
         }
       } else {
-#pragma unroll
+#pragma unroll(C::CHUNK > 0 ? BLOCK_N / 32 : 1)
         for (int c = 0; c < BLOCK_N; c += 32) {
           uint32_t r[32];
           if (C::CHUNK == 0) {
@@ -591,6 +592,9 @@ static int make_tmap(CUtensorMap* map, const bf16* base, long long rows, int col
   return 0;
 }
 
+bool g_profile_on = false;
+std::vector<ProfileEvent> g_profile_events;
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -643,8 +647,18 @@ static int launch(const ConvGemmProblem& p, cudaStream_t stream) {
   const int tiles = kp.num_m_tiles * kp.num_n_tiles;
   if (tiles == 0) return 0;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile_on) {  // bench.py's roofline leg: device time of every launch of this kernel
+    JB_CUDA_OK(cudaEventCreate(&e0));
+    JB_CUDA_OK(cudaEventCreate(&e1));
+    JB_CUDA_OK(cudaEventRecord(e0, stream));
+  }
   kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, kp);
   JB_KERNEL_OK();
+  if (g_profile_on) {
+    JB_CUDA_OK(cudaEventRecord(e1, stream));
+    g_profile_events.push_back({e0, e1, SPLIT ? 1 : 0});
+  }
   return 0;
 }
 

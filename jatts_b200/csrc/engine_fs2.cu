@@ -224,7 +224,7 @@ static int zero_operand_gaps(jatts_fs2* h, const RowLayout& L, cudaStream_t s) {
                                             {h->c_lo, d}, {h->p_hi, pc}, {h->p_lo, pc}, {h->b_hi, od_pad},
                                             {h->b_lo, od_pad}, {h->pa_hi, pn}, {h->pa_lo, pn}, {h->pb_hi, pn},
                                             {h->pb_lo, pn}};
-  for (auto& b : bufs) JB_PROPAGATE(zero_gap_rows(b.p, b.cols * 2, L.frame_mask, 1, L.n_rows, s));
+  for (auto& b : bufs) JB_PROPAGATE(zero_gap_rows(b.p, b.cols * 2, L, 1, s));
   return 0;
 }
 

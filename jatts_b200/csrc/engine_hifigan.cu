@@ -192,12 +192,12 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
   const int in_pad = round_up(c.in_channels, 64);
   const float slope = c.lrelu_slope;
   // mel re-normalisation (vocoder.py:57-61) fused into the operand conversion
-  JB_PROPAGATE(zero_gap_rows(h->mel, in_pad * 2, h->mask, 1, hl.n_rows, s));
+  JB_PROPAGATE(zero_gap_rows(h->mel, in_pad * 2, L, 1, s));
   JB_PROPAGATE(pack_mel_affine(d_mel, c.in_channels, h->mel_scale, h->mel_shift, L, d_off, h->mel, in_pad, s));
   StageIO io{h->mask, 1, hl.n_rows};
   int cur = 0;  // y[cur] holds leaky_relu(stage input)
   {
-    JB_PROPAGATE(zero_gap_rows(h->y[cur], c.channels * 2, h->mask, 1, io.rows, s));
+    JB_PROPAGATE(zero_gap_rows(h->y[cur], c.channels * 2, L, 1, s));
     ConvGemmEpilogue e{};
     e.out_act = h->y[cur]; e.out_act_slope = slope; e.out_act_ld = c.channels;
     JB_PROPAGATE(run_conv(h->input_conv, h->mel, in_pad, io, 1, e, s));
@@ -212,7 +212,7 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
     const int nxt = cur ^ 1;
     // operand buffers of this stage: gap rows must be zero at this rate
     bf16* operands[] = {h->xa0, h->xa, h->t, h->y[nxt]};
-    for (bf16* b : operands) JB_PROPAGATE(zero_gap_rows(b, co * 2, h->mask, io.rate, io.rows, s));
+    for (bf16* b : operands) JB_PROPAGATE(zero_gap_rows(b, co * 2, L, io.rate, s));
     {
       // ConvTranspose1d as a 2-tap polyphase GEMM: tap 0 reads x[j], tap 1 reads x[j-1]
       const ConvW& w = h->ups[i];

@@ -28,19 +28,19 @@ int fill_layout(const int* seg_start, const int* seg_len, int nseg, int n_rows, 
   return 0;
 }
 
-__global__ void zero_gap_rows_kernel(uint4* __restrict__ buf, int row_vec, const uint8_t* __restrict__ mask, int rate,
-                                     long long rows) {
-  const long long r = blockIdx.x;
-  if (r >= rows || mask[r / rate]) return;
+// grid = (gap rows per utterance at this rate, utterances): only the rows that must be zero are touched
+__global__ void zero_gap_rows_kernel(uint4* __restrict__ buf, int row_vec, const int* __restrict__ seg_start,
+                                     const int* __restrict__ seg_len, int rate) {
+  const int b = blockIdx.y;
+  const long long r = (static_cast<long long>(seg_start[b]) + seg_len[b]) * rate + blockIdx.x;
   uint4* p = buf + r * row_vec;
   for (int i = threadIdx.x; i < row_vec; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
 }
-int zero_gap_rows(void* buf, int row_bytes, const uint8_t* frame_mask, int rate, long long rows, cudaStream_t s) {
+int zero_gap_rows(void* buf, int row_bytes, RowLayout L, int rate, cudaStream_t s) {
   JB_REQUIRE(row_bytes % 16 == 0, -2, "zero_gap_rows: row_bytes % 16");
-  if (rows == 0) return 0;
-  JB_REQUIRE(rows < (1ll << 31), -2, "zero_gap_rows: too many rows");
-  zero_gap_rows_kernel<<<static_cast<unsigned>(rows), 64, 0, s>>>(static_cast<uint4*>(buf), row_bytes / 16,
-                                                                  frame_mask, rate, rows);
+  if (L.nseg == 0) return 0;
+  dim3 grid(kGapRows * rate, L.nseg);
+  zero_gap_rows_kernel<<<grid, 64, 0, s>>>(static_cast<uint4*>(buf), row_bytes / 16, L.seg_start, L.seg_len, rate);
   JB_KERNEL_OK();
   return 0;
 }

@@ -21,6 +21,7 @@ from . import _lib, _pack
 
 
 def _hifigan_shapes(cfg: dict) -> "OrderedDict[str, tuple]":
+    """parallel_wavegan HiFiGANGenerator key order: input_conv, upsamples.*, blocks.* (convs1 then convs2), output_conv"""
     s: "OrderedDict[str, tuple]" = OrderedDict()
     ch, k = cfg["channels"], cfg["kernel_size"]
     s["input_conv.weight"] = (ch, cfg["in_channels"], k)
@@ -28,11 +29,13 @@ def _hifigan_shapes(cfg: dict) -> "OrderedDict[str, tuple]":
     nb = len(cfg["resblock_kernel_sizes"])
     for i, (sc, uk) in enumerate(zip(cfg["upsample_scales"], cfg["upsample_kernel_sizes"])):
         ci, co = ch // (2 ** i), ch // (2 ** (i + 1))
-        s[f"upsamples.{i}.1.weight"] = (ci, co, uk)
+        s[f"upsamples.{i}.1.weight"] = (ci, co, uk)  # ConvTranspose1d layout (C_in, C_out, k)
         s[f"upsamples.{i}.1.bias"] = (co,)
+    for i in range(len(cfg["upsample_scales"])):
+        co = ch // (2 ** (i + 1))
         for j, (rk, dils) in enumerate(zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilations"])):
-            for d in range(len(dils)):
-                for cv in ("convs1", "convs2"):
+            for cv in ("convs1", "convs2"):
+                for d in range(len(dils)):
                     s[f"blocks.{i * nb + j}.{cv}.{d}.1.weight"] = (co, co, rk)
                     s[f"blocks.{i * nb + j}.{cv}.{d}.1.bias"] = (co,)
     cl = ch // (2 ** len(cfg["upsample_scales"]))

@@ -222,6 +222,7 @@ def make_spembs(n: int, seed: int, dim: int = 192) -> torch.Tensor:
 # HiFi-GAN weights (weight-norm already removed; parallel_wavegan state_dict names)
 # --------------------------------------------------------------------------------------------
 def hifigan_state_shapes(cfg: dict) -> "OrderedDict[str, tuple]":
+    """parallel_wavegan HiFiGANGenerator key order: input_conv, upsamples.*, blocks.* (convs1 then convs2), output_conv"""
     s: "OrderedDict[str, tuple]" = OrderedDict()
     ch, k = cfg["channels"], cfg["kernel_size"]
     s["input_conv.weight"] = (ch, cfg["in_channels"], k)
@@ -231,13 +232,13 @@ def hifigan_state_shapes(cfg: dict) -> "OrderedDict[str, tuple]":
         ci, co = ch // (2 ** i), ch // (2 ** (i + 1))
         s[f"upsamples.{i}.1.weight"] = (ci, co, uk)  # ConvTranspose1d layout (C_in, C_out, k)
         s[f"upsamples.{i}.1.bias"] = (co,)
+    for i in range(len(cfg["upsample_scales"])):
+        co = ch // (2 ** (i + 1))
         for j, (rk, dils) in enumerate(zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilations"])):
-            for d in range(len(dils)):
-                s[f"blocks.{i * nb + j}.convs1.{d}.1.weight"] = (co, co, rk)
-                s[f"blocks.{i * nb + j}.convs1.{d}.1.bias"] = (co,)
-                if cfg["use_additional_convs"]:
-                    s[f"blocks.{i * nb + j}.convs2.{d}.1.weight"] = (co, co, rk)
-                    s[f"blocks.{i * nb + j}.convs2.{d}.1.bias"] = (co,)
+            for cv in ("convs1", "convs2"):
+                for d in range(len(dils)):
+                    s[f"blocks.{i * nb + j}.{cv}.{d}.1.weight"] = (co, co, rk)
+                    s[f"blocks.{i * nb + j}.{cv}.{d}.1.bias"] = (co,)
     cl = ch // (2 ** len(cfg["upsample_scales"]))
     s["output_conv.1.weight"] = (cfg["out_channels"], cl, k)
     s["output_conv.1.bias"] = (cfg["out_channels"],)
