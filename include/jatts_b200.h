@@ -129,7 +129,7 @@ typedef struct {
   int32_t up_s, up_p, up_cout;
   const float* d_bias; int32_t act; float slope, scale;
   const float* d_res_f32; const void* d_res_bf16; int32_t res_ld;
-  const float* d_accum_in; float post_scale;
+  const float* d_accum_in; const void* d_accum_bf16; float post_scale;
   float* d_out_f32; int32_t out_f32_ld;
   void* d_out_hi; void* d_out_lo; int32_t out_bf_ld;
   void* d_out_act; float out_act_slope; int32_t out_act_ld;

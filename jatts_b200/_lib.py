@@ -47,7 +47,7 @@ class ConvGemmArgs(C.Structure):
         ("up_s", C.c_int32), ("up_p", C.c_int32), ("up_cout", C.c_int32),
         ("d_bias", C.c_void_p), ("act", C.c_int32), ("slope", C.c_float), ("scale", C.c_float),
         ("d_res_f32", C.c_void_p), ("d_res_bf16", C.c_void_p), ("res_ld", C.c_int32),
-        ("d_accum_in", C.c_void_p), ("post_scale", C.c_float),
+        ("d_accum_in", C.c_void_p), ("d_accum_bf16", C.c_void_p), ("post_scale", C.c_float),
         ("d_out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("d_out_hi", C.c_void_p), ("d_out_lo", C.c_void_p), ("out_bf_ld", C.c_int32),
         ("d_out_act", C.c_void_p), ("out_act_slope", C.c_float), ("out_act_ld", C.c_int32),

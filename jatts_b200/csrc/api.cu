@@ -22,7 +22,7 @@ extern "C" int jatts_op_conv_gemm(const jatts_conv_gemm_args* a, int32_t impl, v
   ConvGemmEpilogue& e = p.ep;
   e.bias = a->d_bias; e.act = a->act; e.slope = a->slope; e.scale = a->scale;
   e.res_f32 = a->d_res_f32; e.res_bf16 = static_cast<const bf16*>(a->d_res_bf16); e.res_ld = a->res_ld;
-  e.accum_in = a->d_accum_in; e.post_scale = a->post_scale;
+  e.accum_in = a->d_accum_in; e.accum_bf16 = static_cast<const bf16*>(a->d_accum_bf16); e.post_scale = a->post_scale;
   e.out_f32 = a->d_out_f32; e.out_f32_ld = a->out_f32_ld;
   e.out_hi = static_cast<bf16*>(a->d_out_hi); e.out_lo = static_cast<bf16*>(a->d_out_lo); e.out_bf_ld = a->out_bf_ld;
   e.out_act = static_cast<bf16*>(a->d_out_act); e.out_act_slope = a->out_act_slope; e.out_act_ld = a->out_act_ld;

@@ -24,7 +24,8 @@ struct ConvGemmEpilogue {
   const float* res_f32;     // v += res_f32[row*res_ld + n]
   const bf16* res_bf16;     // v += res_bf16[row*res_ld + n]
   int res_ld;
-  const float* accum_in;    // v += accum_in[row*out_f32_ld + n]   (MRF branch sum)
+  const float* accum_in;    // v += accum_in[row*out_f32_ld + n]   (fp32 running sum)
+  const bf16* accum_bf16;   // v += accum_bf16[row*res_ld + n]     (MRF branch sum kept in bf16)
   float post_scale;         // v *= post_scale
   float* out_f32;           // optional fp32 output
   int out_f32_ld;
@@ -57,8 +58,11 @@ struct ConvGemmProblem {
   ConvGemmEpilogue ep;
 };
 
-// Launch the tcgen05 kernel.  Returns 0 / negative JATTS_E_*.
+// Launch the tcgen05 kernel (dispatches to the TMA-epilogue variant of conv_gemm_tc2.cu when the
+// problem is a plain bf16 convolution with bf16 inputs/outputs).  Returns 0 / negative JATTS_E_*.
 int conv_gemm_tc(const ConvGemmProblem& p, cudaStream_t stream);
+bool conv_gemm_tc2_eligible(const ConvGemmProblem& p);
+int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream);
 // Plain CUDA-core kernel with identical semantics; used ONLY by the test entry point to bisect
 // tensor-core kernel bugs from host-side packing bugs.  Never on the product path.
 int conv_gemm_simt_debug(const ConvGemmProblem& p, cudaStream_t stream);

@@ -23,8 +23,7 @@ struct jatts_hifigan {
 
   Arena arena;
   int cap_rows = 0, cap_utt = 0;
-  bf16 *mel, *x0, *xa0, *x, *xa, *t, *y[2];
-  float* sum;
+  bf16 *mel, *x0, *xa0, *x, *xa, *t, *y[2], *sum;
   uint8_t* mask;
   int *seg, *d_small = nullptr, *h_small = nullptr;
   cudaEvent_t staged = nullptr;
@@ -49,7 +48,7 @@ static int ensure_workspace(jatts_hifigan* h, int rows, int n_utt) {
   size_t per_row = static_cast<size_t>(c.channels);  // stage input of stage 0: [rows, channels]
   for (size_t i = 0; i < h->rate.size(); ++i) per_row = std::max(per_row, static_cast<size_t>(h->rate[i]) * h->chans[i]);
   const size_t in_pad = round_up(c.in_channels, 64);
-  size_t bytes = Arena::padded(2 * R * in_pad) + 7 * Arena::padded(2 * R * per_row) + Arena::padded(4 * R * per_row) +
+  size_t bytes = Arena::padded(2 * R * in_pad) + 8 * Arena::padded(2 * R * per_row) +
                  Arena::padded(R) + Arena::padded(4 * R);
   JB_PROPAGATE(h->arena.reserve(bytes));
   Arena& a = h->arena;
@@ -59,7 +58,7 @@ static int ensure_workspace(jatts_hifigan* h, int rows, int n_utt) {
   h->x = a.take<bf16>(R * per_row); h->xa = a.take<bf16>(R * per_row);
   h->t = a.take<bf16>(R * per_row);
   h->y[0] = a.take<bf16>(R * per_row); h->y[1] = a.take<bf16>(R * per_row);
-  h->sum = a.take<float>(R * per_row);
+  h->sum = a.take<bf16>(R * per_row);
   h->mask = a.take<uint8_t>(R);
   h->seg = a.take<int>(R);
   h->cap_rows = static_cast<int>(R);
@@ -244,10 +243,9 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
         } else {
           // branch output: accumulate the mean over residual blocks; the last block emits the next
           // layer's operand leaky_relu(mean) directly
-          e2.out_f32_ld = co;
-          if (j > 0) e2.accum_in = h->sum;
+          if (j > 0) e2.accum_bf16 = h->sum;
           if (j + 1 < c.n_resblocks) {
-            e2.out_f32 = h->sum;
+            e2.out_hi = h->sum; e2.out_bf_ld = co;
           } else {
             e2.post_scale = 1.0f / c.n_resblocks;
             e2.out_act = h->y[nxt]; e2.out_act_slope = next_slope; e2.out_act_ld = co;

@@ -20,6 +20,11 @@ CASES = {
     "conv_k11_d5":     (dict(m=700, c_in=64, n=64, taps=11, dil=5, block_n=64, act=A.ACT_LRELU, out=("hi",)), 1e-4),
     "conv_k7_d3_res":  (dict(m=400, c_in=128, n=128, taps=7, dil=3, res="bf16", out=("hi", "act")), 1e-4),
     "conv_accum":      (dict(m=300, c_in=64, n=64, taps=3, block_n=64, res="bf16", accum=True, post_scale=1 / 3, out=("f32", "act")), 1e-4),
+    "tma_ep_res_acc":  (dict(m=900, c_in=64, n=64, taps=7, dil=3, block_n=64, res="bf16", accum="bf16", post_scale=1 / 3, mask_rate=5, out=("hi", "act")), 1e-4),
+    "tma_ep_c32":      (dict(m=1300, c_in=32, n=32, taps=11, dil=5, block_n=32, res="bf16", act=A.ACT_LRELU, mask_rate=3, out=("hi", "act")), 1e-4),
+    "tma_ep_c256":     (dict(m=128 * 7 + 5, c_in=256, n=256, taps=3, block_n=256, res="bf16", accum="bf16", out=("hi",)), 1e-4),
+    "tma_ep_n512":     (dict(m=300, c_in=80, n=512, taps=7, block_n=256, a_ld=128, out=("act",)), 1e-4),
+    "tma_ep_c128_many": (dict(m=128 * 300 + 77, c_in=128, n=128, taps=3, block_n=128, res="bf16", mask_rate=25, out=("hi", "act")), 1e-4),
     "conv_masked":     (dict(m=1000, c_in=64, n=64, taps=3, block_n=64, mask_rate=25, out=("f32", "hi", "act")), 1e-4),
     "split_gemm":      (dict(m=333, c_in=384, n=384, split_mode=True, res="f32", scale=0.5), 2e-5),
     "split_conv_k3":   (dict(m=450, c_in=384, n=1536, taps=3, split_mode=True, act=A.ACT_RELU, out=("f32", "hi", "lo")), 2e-5),
