@@ -1,6 +1,13 @@
 // conv_bf16_tma_kernel: the HiFi-GAN convolution kernel (bf16 operands, fp32 TMEM accumulation) with a
-// TMA-staged epilogue.  Same implicit-GEMM mainloop as conv_gemm_tc_kernel (TMA producer warp,
-// single-thread tcgen05.mma issuer, TMEM double buffer); what changes is how a finished tile leaves:
+// TMA-staged epilogue and three mainloop modes:
+//   STREAM    one [128 x KCH] activation tile + one [N x KCH] weight tile per (tap, K chunk) stage
+//   HALO      one activation SLAB per K chunk = tile rows + the taps' halo; each tap is an MMA whose A
+//             descriptor starts tap*dilation rows into the slab (128B/64B swizzle is a function of the
+//             absolute smem address, so row-shifted starts need no base_offset -- measured); weights
+//             stream through their own ring
+//   RESIDENT  HALO + all taps' weights loaded into smem once per CTA: no per-tap barrier traffic at
+//             all (the single-thread MMA issuer was the bottleneck for C <= 64: 88 clk per 16-clk MMA)
+// Epilogue (all modes):
 //
 //   warp 2      epilogue loader: TMA-loads the residual / branch-sum tiles of upcoming tiles into a
 //               ring of swizzled smem slabs (so no epilogue thread ever waits on a global load)
@@ -12,15 +19,17 @@
 // (tensor pipe 5 %, DRAM 2-9 %, profiles/r01_summary.md); here every global access of the kernel is a
 // bulk asynchronous copy.  Rows that do not belong to an utterance are stored as zeros (the packed
 // layout needs its gap rows to stay zero); rows past the end of the tensor are clipped by TMA.
+#include <cstdlib>
+
 #include "conv_gemm.cuh"
 #include "tc_common.cuh"
 
 namespace jb {
 
 static constexpr int BLOCK_M2 = 128;
-static constexpr int BLOCK_K2 = 64;
 static constexpr int UMMA_K2 = 16;
 static constexpr int kThreads2 = 256;
+enum : int { MODE_STREAM = 0, MODE_HALO = 1, MODE_RESIDENT = 2 };
 
 struct KernelParams2 {
   int taps, k_chunks, n_pad;
@@ -35,9 +44,10 @@ struct KernelParams2 {
   float post_scale;
   float out1_slope;
   int has_res, has_acc, has_out0, has_out1;
+  int halo_rows;    // HALO/RESIDENT: rows of the activation box (128 + (taps-1)*tap_stride, padded to 8)
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KCH, int MODE>
 struct Cfg2 {
   static constexpr int SLAB = BLOCK_N >= 64 ? 64 : 32;     // columns per epilogue slab
   static constexpr int N_SLABS = BLOCK_N / SLAB;
@@ -45,45 +55,79 @@ struct Cfg2 {
   static constexpr int SW_MASK = ROWB == 128 ? 7 : 3;       // Swizzle<3,4,3> / Swizzle<2,4,3>
   static constexpr int SLAB_BYTES = BLOCK_M2 * ROWB;
   static constexpr int ENTRY_BYTES = 2 * SLAB_BYTES;        // [residual -> out0 | branch sum -> out1]
-  static constexpr int EP_ENTRIES = BLOCK_N == 256 ? 2 : (BLOCK_N == 32 ? 4 : 3);
-  static constexpr int A_BYTES = BLOCK_M2 * BLOCK_K2 * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K2 * 2;
+  static constexpr int EP_ENTRIES = MODE == MODE_RESIDENT ? (BLOCK_N == 32 ? 4 : 2)
+                                                          : (BLOCK_N == 256 ? 2 : (BLOCK_N == 32 ? 4 : 3));
+  static constexpr int KROWB = KCH * 2;                     // operand row bytes (128 or 64) = swizzle span
+  static constexpr int A_BYTES = BLOCK_M2 * KROWB;
+  static constexpr int B_BYTES = BLOCK_N * KROWB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BIAS_BYTES = 2048;                   // n_pad <= 512
-  static constexpr int BAR_BYTES = 512;
-  static constexpr int BUDGET = 225 * 1024 - EP_ENTRIES * ENTRY_BYTES - BIAS_BYTES - BAR_BYTES - 1024;
+  static constexpr int BAR_BYTES = 1024;                    // keeps the resident weight area 1024-aligned
+  static constexpr int FIXED_TAIL = EP_ENTRIES * ENTRY_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  static constexpr int BUDGET = 225 * 1024 - FIXED_TAIL;
+  // STREAM
   static constexpr int MAX_STAGES = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EP_ENTRIES * ENTRY_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  // HALO / RESIDENT: activation slabs [HALO_MAX_ROWS x KCH]
+  static constexpr int HALO_MAX_ROWS = 192;                 // 128 + (11-1)*5 = 178, padded
+  static constexpr int A_SLAB_BYTES = HALO_MAX_ROWS * KROWB;  // multiple of 1024
+  static constexpr int A_STAGES = MODE == MODE_RESIDENT ? (BLOCK_N == 32 ? 4 : 2) : (BLOCK_N == 256 ? 2 : 3);
+  static constexpr int B_MAX = (BUDGET - A_STAGES * A_SLAB_BYTES) / B_BYTES;
+  static constexpr int B_STAGES = B_MAX > 8 ? 8 : B_MAX;
+  static constexpr int MAIN_BYTES = MODE == MODE_STREAM ? STAGES * STAGE_BYTES
+                                  : MODE == MODE_HALO   ? A_STAGES * A_SLAB_BYTES + B_STAGES * B_BYTES
+                                                        : A_STAGES * A_SLAB_BYTES;
+  static constexpr int SMEM_FIXED = MAIN_BYTES + FIXED_TAIL;   // + resident weight bytes in RESIDENT mode
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static_assert(MODE != MODE_STREAM || STAGES >= 2, "stream pipeline depth");
+  static_assert(MODE != MODE_HALO || B_STAGES >= 2, "weight ring depth");
+  static_assert(A_STAGES <= 4 && STAGES <= 8 && B_STAGES <= 8, "barrier arrays");
 };
 
-template <int BLOCK_N>
+// K-major operand tile with rows of exactly one swizzle span (128 B: KCH = 64, 64 B: KCH = 32)
+template <int KCH>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8 * KCH * 2) >> 4) << 32;    // SBO: 8 rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(KCH == 64 ? 2 : 4) << 61;     // SWIZZLE_128B / SWIZZLE_64B
+  return d;
+}
+
+template <int BLOCK_N, int KCH, int MODE>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_acc,
                      const __grid_constant__ CUtensorMap tm_out0, const __grid_constant__ CUtensorMap tm_out1,
                      const __grid_constant__ KernelParams2 P) {
-  using C = Cfg2<BLOCK_N>;
+  using C = Cfg2<BLOCK_N, KCH, MODE>;
   constexpr int STAGES = C::STAGES;
   constexpr int E = C::EP_ENTRIES;
+  constexpr int KSTEPS = KCH / UMMA_K2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ep_base = smem + STAGES * C::STAGE_BYTES;                 // 1024-aligned (all sizes are multiples)
+  uint8_t* b_base = smem + C::A_STAGES * C::A_SLAB_BYTES;             // HALO: weight ring after the A slabs
+  uint8_t* ep_base = smem + C::MAIN_BYTES;                            // 1024-aligned (all sizes are multiples)
   float* bias_s = reinterpret_cast<float*>(ep_base + E * C::ENTRY_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + C::BIAS_BYTES);
-  uint64_t* full_bar = bars;                    // [STAGES]
-  uint64_t* empty_bar = full_bar + STAGES;      // [STAGES]
-  uint64_t* tfull_bar = empty_bar + STAGES;     // [2]
+  uint8_t* w_base = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;  // RESIDENT: all weight tiles (1024-aligned)
+  constexpr int NB = 8;
+  uint64_t* full_bar = bars;                    // [NB]   STREAM: A+B stage | HALO: weight ring
+  uint64_t* empty_bar = full_bar + NB;          // [NB]
+  uint64_t* afull_bar = empty_bar + NB;         // [4]    HALO/RESIDENT: activation slabs
+  uint64_t* aempty_bar = afull_bar + 4;         // [4]
+  uint64_t* tfull_bar = aempty_bar + 4;         // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
   uint64_t* epfull_bar = tempty_bar + 2;        // [E]
   uint64_t* epempty_bar = epfull_bar + E;       // [E]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epempty_bar + E);
+  uint64_t* wfull_bar = epempty_bar + E;        // [1]    RESIDENT: weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = P.num_m_tiles * P.num_n_tiles;
-  const int k_iters = P.taps * P.k_chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -92,9 +136,13 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (P.has_acc) tma_prefetch_desc(&tm_acc);
     if (P.has_out0) tma_prefetch_desc(&tm_out0);
     if (P.has_out1) tma_prefetch_desc(&tm_out1);
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NB; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -104,6 +152,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       mbar_init(&epfull_bar[i], 1);
       mbar_init(&epempty_bar[i], 1);
     }
+    mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -121,21 +170,52 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   if (warp == 0) {
     // ===================== mainloop TMA producer =====================
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
-        const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
-        for (int tap = 0; tap < P.taps; ++tap) {
-          const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
-          const int brow = tap * P.n_pad + n0;
+      if (MODE == MODE_STREAM) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
+          const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+          for (int tap = 0; tap < P.taps; ++tap) {
+            const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
+            const int brow = tap * P.n_pad + n0;
+            for (int kc = 0; kc < P.k_chunks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* s = smem + stage * C::STAGE_BYTES;
+              mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+              tma_load_2d(&tm_a, &full_bar[stage], s, kc * KCH, arow);
+              tma_load_2d(&tm_b, &full_bar[stage], s + C::A_BYTES, kc * KCH, brow);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else {
+        if (MODE == MODE_RESIDENT) {
+          // every weight tile of this convolution, once per CTA (num_n_tiles == 1 in this mode)
+          mbar_expect_tx(wfull_bar, static_cast<uint32_t>(P.taps * P.k_chunks) * C::B_BYTES);
+          for (int kc = 0; kc < P.k_chunks; ++kc)
+            for (int tap = 0; tap < P.taps; ++tap)
+              tma_load_2d(&tm_b, wfull_bar, w_base + (kc * P.taps + tap) * C::B_BYTES, kc * KCH, tap * P.n_pad);
+        }
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * C::KROWB;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
+          const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
           for (int kc = 0; kc < P.k_chunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* s = smem + stage * C::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            tma_load_2d(&tm_a, &full_bar[stage], s, kc * BLOCK_K2, arow);
-            tma_load_2d(&tm_b, &full_bar[stage], s + C::A_BYTES, kc * BLOCK_K2, brow);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            mbar_wait(&aempty_bar[as], aph ^ 1);
+            mbar_expect_tx(&afull_bar[as], a_bytes);
+            tma_load_2d(&tm_a, &afull_bar[as], smem + as * C::A_SLAB_BYTES, kc * KCH, m0 + P.tap_off0);
+            if (++as == C::A_STAGES) { as = 0; aph ^= 1; }
+            if (MODE == MODE_HALO) {
+              for (int tap = 0; tap < P.taps; ++tap) {
+                mbar_wait(&empty_bar[bs], bph ^ 1);
+                mbar_expect_tx(&full_bar[bs], C::B_BYTES);
+                tma_load_2d(&tm_b, &full_bar[bs], b_base + bs * C::B_BYTES, kc * KCH, tap * P.n_pad + n0);
+                if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+              }
+            }
           }
         }
       }
@@ -144,30 +224,80 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
-      int stage = 0;
-      uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+      if (MODE == MODE_STREAM) {
+        const int k_iters = P.taps * P.k_chunks;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint64_t da = make_sw128_desc(sa);
-          const uint64_t db = make_sw128_desc(sa + C::A_BYTES);
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+          for (int it = 0; it < k_iters; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint64_t da = make_kmajor_desc<KCH>(sa);
+            const uint64_t db = make_kmajor_desc<KCH>(sa + C::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K2 / UMMA_K2; ++k) {
-            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K2 * 2) >> 4);
-            tc_mma_bf16(tmem_d, da + koff, db + koff, idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < KSTEPS; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K2 * 2) >> 4);
+              tc_mma_bf16(tmem_d, da + koff, db + koff, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tc_commit(&tfull_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      } else {
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        if (MODE == MODE_RESIDENT) {
+          mbar_wait(wfull_bar, 0);
+          tc_fence_after();
+        }
+        const uint32_t w_addr = smem_u32(w_base);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+          for (int kc = 0; kc < P.k_chunks; ++kc) {
+            mbar_wait(&afull_bar[as], aph);
+            tc_fence_after();
+            const uint32_t slab = smem_u32(smem + as * C::A_SLAB_BYTES);
+            for (int tap = 0; tap < P.taps; ++tap) {
+              uint32_t b_addr;
+              if (MODE == MODE_HALO) {
+                mbar_wait(&full_bar[bs], bph);
+                tc_fence_after();
+                b_addr = smem_u32(b_base + bs * C::B_BYTES);
+              } else {
+                b_addr = w_addr + static_cast<uint32_t>(kc * P.taps + tap) * C::B_BYTES;
+              }
+              // tap t reads activation rows [t*dilation, t*dilation + 128) of the slab: a row-shifted
+              // start address.  Measured on B200: the swizzle is a function of the absolute smem address
+              // bits, so a start that is not 1024 B aligned needs NO base_offset in the descriptor.
+              const uint32_t a_addr = slab + static_cast<uint32_t>(tap * P.tap_stride) * C::KROWB;
+              const uint64_t da = make_kmajor_desc<KCH>(a_addr);
+              const uint64_t db = make_kmajor_desc<KCH>(b_addr);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint64_t koff = static_cast<uint64_t>((k * UMMA_K2 * 2) >> 4);
+                tc_mma_bf16(tmem_d, da + koff, db + koff, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              }
+              if (MODE == MODE_HALO) {
+                tc_commit(&empty_bar[bs]);
+                if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+              }
+            }
+            tc_commit(&aempty_bar[as]);
+            if (++as == C::A_STAGES) { as = 0; aph ^= 1; }
+          }
+          tc_commit(&tfull_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
       }
     }
   } else if (warp == 2) {
@@ -330,15 +460,17 @@ bool conv_gemm_tc2_eligible(const ConvGemmProblem& p) {
   return true;
 }
 
-template <int BLOCK_N>
+
+template <int BLOCK_N, int KCH, int MODE>
 static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
-  using C = Cfg2<BLOCK_N>;
-  static_assert(C::STAGES >= 2, "need at least a double buffer");
+  using C = Cfg2<BLOCK_N, KCH, MODE>;
   const ConvGemmEpilogue& e = p.ep;
   CUtensorMap ta, tb, tres, tacc, to0, to1;
   const int a_cols = p.a_cols > 0 ? p.a_cols : p.k_pad;
-  JB_PROPAGATE(make_tmap(&ta, p.a_hi, p.a_rows, a_cols, p.a_ld, BLOCK_M2));
-  JB_PROPAGATE(make_tmap(&tb, p.w_hi, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BLOCK_N));
+  const int k_chunks = ceil_div(a_cols, KCH);   // channel padding beyond a_cols is all-zero: skip it
+  const int halo_rows = round_up(BLOCK_M2 + (p.taps - 1) * p.tap_stride, 8);
+  JB_PROPAGATE(make_tmap(&ta, p.a_hi, p.a_rows, a_cols, p.a_ld, MODE == MODE_STREAM ? BLOCK_M2 : halo_rows, KCH));
+  JB_PROPAGATE(make_tmap(&tb, p.w_hi, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BLOCK_N, KCH));
   tres = tacc = to0 = to1 = ta;
   if (e.res_bf16) JB_PROPAGATE(make_tmap(&tres, e.res_bf16, p.m_rows, p.n, e.res_ld, BLOCK_M2, C::SLAB));
   if (e.accum_bf16) JB_PROPAGATE(make_tmap(&tacc, e.accum_bf16, p.m_rows, p.n, e.res_ld, BLOCK_M2, C::SLAB));
@@ -346,7 +478,7 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   if (e.out_act) JB_PROPAGATE(make_tmap(&to1, e.out_act, p.m_rows, p.n, e.out_act_ld, BLOCK_M2, C::SLAB));
   KernelParams2 kp;
   kp.taps = p.taps;
-  kp.k_chunks = p.k_pad / BLOCK_K2;
+  kp.k_chunks = k_chunks;
   kp.n_pad = p.n_pad;
   kp.tap_off0 = p.tap_off0;
   kp.tap_stride = p.tap_stride;
@@ -364,11 +496,15 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.has_acc = e.accum_bf16 != nullptr;
   kp.has_out0 = e.out_hi != nullptr;
   kp.has_out1 = e.out_act != nullptr;
-  auto kern = conv_bf16_tma_kernel<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+  kp.halo_rows = halo_rows;
+  const int w_bytes = MODE == MODE_RESIDENT ? p.taps * k_chunks * C::B_BYTES : 0;
+  const int smem_bytes = C::SMEM_FIXED + w_bytes;
+  JB_REQUIRE(smem_bytes <= 227 * 1024, -2, "conv_gemm_tc2: shared memory budget exceeded");
+  auto kern = conv_bf16_tma_kernel<BLOCK_N, KCH, MODE>;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_bytes = smem_bytes;
   }
   const int tiles = kp.num_m_tiles * kp.num_n_tiles;
   if (tiles == 0) return 0;
@@ -379,7 +515,7 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  kern<<<grid, kThreads2, C::SMEM_BYTES, stream>>>(ta, tb, tres, tacc, to0, to1, kp);
+  kern<<<grid, kThreads2, smem_bytes, stream>>>(ta, tb, tres, tacc, to0, to1, kp);
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));
@@ -389,11 +525,32 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
 }
 
 int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream) {
+  static const int max_mode = getenv("JATTS_B200_TC2_MODE") ? atoi(getenv("JATTS_B200_TC2_MODE")) : 2;  // A/B switch
+  const int a_cols = p.a_cols > 0 ? p.a_cols : p.k_pad;
+  const bool halo_ok = max_mode >= MODE_HALO && p.taps > 1 && p.tap_stride > 0 &&
+                       round_up(BLOCK_M2 + (p.taps - 1) * p.tap_stride, 8) <= 192;
+  // RESIDENT when every weight tile of the convolution fits next to the pipeline buffers
+  auto resident_ok = [&](int fixed, int b_bytes, int kch) {
+    return halo_ok && max_mode >= MODE_RESIDENT && p.n_pad == p.block_n &&
+           fixed + p.taps * ceil_div(a_cols, kch) * b_bytes <= 227 * 1024;
+  };
   switch (p.block_n) {
-    case 32: return launch2<32>(p, stream);
-    case 64: return launch2<64>(p, stream);
-    case 128: return launch2<128>(p, stream);
-    case 256: return launch2<256>(p, stream);
+    case 32:
+      if (a_cols <= 32 && resident_ok(Cfg2<32, 32, MODE_RESIDENT>::SMEM_FIXED, Cfg2<32, 32, MODE_RESIDENT>::B_BYTES, 32))
+        return launch2<32, 32, MODE_RESIDENT>(p, stream);
+      if (resident_ok(Cfg2<32, 64, MODE_RESIDENT>::SMEM_FIXED, Cfg2<32, 64, MODE_RESIDENT>::B_BYTES, 64))
+        return launch2<32, 64, MODE_RESIDENT>(p, stream);
+      return launch2<32, 64, MODE_STREAM>(p, stream);
+    case 64:
+      if (resident_ok(Cfg2<64, 64, MODE_RESIDENT>::SMEM_FIXED, Cfg2<64, 64, MODE_RESIDENT>::B_BYTES, 64))
+        return launch2<64, 64, MODE_RESIDENT>(p, stream);
+      return launch2<64, 64, MODE_STREAM>(p, stream);
+    case 128:
+      if (resident_ok(Cfg2<128, 64, MODE_RESIDENT>::SMEM_FIXED, Cfg2<128, 64, MODE_RESIDENT>::B_BYTES, 64))
+        return launch2<128, 64, MODE_RESIDENT>(p, stream);
+      return halo_ok ? launch2<128, 64, MODE_HALO>(p, stream) : launch2<128, 64, MODE_STREAM>(p, stream);
+    case 256:
+      return halo_ok ? launch2<256, 64, MODE_HALO>(p, stream) : launch2<256, 64, MODE_STREAM>(p, stream);
   }
   return -2;
 }
