@@ -122,7 +122,8 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
   uint64_t* epfull_bar = tempty_bar + 2;        // [E]
   uint64_t* epempty_bar = epfull_bar + E;       // [E]
-  uint64_t* wfull_bar = epempty_bar + E;        // [1]    RESIDENT: weights landed
+  uint64_t* ready_bar = epempty_bar + E;        // [E]    epilogue -> store warp: slab written
+  uint64_t* wfull_bar = ready_bar + E;          // [1]    RESIDENT: weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -151,6 +152,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     for (int i = 0; i < E; ++i) {
       mbar_init(&epfull_bar[i], 1);
       mbar_init(&epempty_bar[i], 1);
+      mbar_init(&ready_bar[i], 128);
     }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -323,6 +325,27 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
       }
     }
+  } else if (warp == 3) {
+    // ===================== store warp: slab -> global by TMA =====================
+    if (elect_one()) {
+      int e = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
+        const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+        for (int s = 0; s < C::N_SLABS; ++s) {
+          mbar_wait(&ready_bar[e], ph);      // all 128 epilogue threads wrote + fenced this slab
+          uint8_t* bufA = ep_base + e * C::ENTRY_BYTES;
+          if (P.has_out0) tma_store_2d(&tm_out0, bufA, n0 + s * C::SLAB, m0);
+          if (P.has_out1) tma_store_2d(&tm_out1, bufA + C::SLAB_BYTES, n0 + s * C::SLAB, m0);
+          tma_store_commit();
+          tma_store_wait_read<0>();          // smem has been read: the entry can be refilled
+          mbar_arrive(&epempty_bar[e]);
+          if (++e == E) { e = 0; ph ^= 1; }
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (warps 4..7) =====================
     const int lane_group = warp & 3;
@@ -330,18 +353,23 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
     const uint32_t row_off = static_cast<uint32_t>(row_in_tile * C::ROWB);
     const uint32_t sw = (row_off >> 7) & C::SW_MASK;   // XOR pattern of this row's 16-byte chunks
-    const bool issuer = (warp == 4 && lane == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     int e = 0;
     uint32_t ph = 0;
-    int groups = 0;  // bulk store groups committed by the issuer
+    // row validity of the NEXT tile is fetched while the current one is processed (one global byte per
+    // thread per tile; its latency used to sit on the per-tile critical path)
+    auto row_valid = [&](int tile) -> bool {
+      if (tile >= num_tiles) return false;
+      const int row = (tile / P.num_n_tiles) * BLOCK_M2 + row_in_tile;
+      if (row >= P.m_rows) return false;
+      return P.frame_mask ? P.frame_mask[row / P.rate] != 0 : true;
+    };
+    bool valid_next = row_valid(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
       const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
-      const int row = m0 + row_in_tile;
-      bool valid = row < P.m_rows;
-      if (valid && P.frame_mask) valid = P.frame_mask[row / P.rate] != 0;   // issued before the accumulator wait
+      const bool valid = valid_next;
+      valid_next = row_valid(tile + gridDim.x);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -413,21 +441,11 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         fence_proxy_async_smem();            // make the generic-proxy smem writes visible to the TMA engine
-        named_bar_sync(1, 128);
-        if (issuer) {
-          if (P.has_out0) tma_store_2d(&tm_out0, bufA, n0 + s * C::SLAB, m0);
-          if (P.has_out1) tma_store_2d(&tm_out1, bufB, n0 + s * C::SLAB, m0);
-          tma_store_commit();
-          ++groups;
-          // the store issued E-1 groups ago has finished reading its slab: release that entry
-          tma_store_wait_read<E - 1>();
-          if (groups >= E) mbar_arrive(&epempty_bar[(e + 1) % E]);
-        }
+        mbar_arrive(&ready_bar[e]);          // hand the slab to the store warp; nobody waits here
         if (++e == E) { e = 0; ph ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
   }
 
   tc_fence_before();
