@@ -68,6 +68,9 @@ JATTS_API int64_t jatts_launch_count(void);
 JATTS_API int jatts_profile_begin(void);
 JATTS_API int jatts_profile_end(double* ms_bf16, int64_t* n_bf16, double* ms_split, int64_t* n_split);
 
+/* debug: per-role clock64 timeline of CTA 0 of the TMA-epilogue convolution kernel (d_buf: 5*8*64 int64, or NULL) */
+JATTS_API int jatts_debug_set_trace(void* d_buf);
+
 /* ---- FastSpeech2 (replaces jatts/models/fastspeech2.py:566-735 on the inference path) ------------ */
 typedef struct {
   int32_t idim, odim, adim, aheads;

@@ -57,3 +57,10 @@ extern "C" int jatts_profile_end(double* ms_bf16, int64_t* n_bf16, double* ms_sp
   if (n_split) *n_split = n[1];
   return 0;
 }
+
+namespace jb { extern long long* g_trace_ptr; }
+// debug only: device buffer of 5*8*64 int64 that CTA 0 of the TMA-epilogue conv kernel fills with clock64 stamps
+extern "C" int jatts_debug_set_trace(void* d_buf) {
+  jb::g_trace_ptr = static_cast<long long*>(d_buf);
+  return 0;
+}

@@ -28,7 +28,7 @@ namespace jb {
 
 static constexpr int BLOCK_M2 = 128;
 static constexpr int UMMA_K2 = 16;
-static constexpr int kThreads2 = 256;
+static constexpr int kThreads2 = 416;  // producer, MMA x2 (warps 1, 12), loader, store, 8 epilogue warps
 enum : int { MODE_STREAM = 0, MODE_HALO = 1, MODE_RESIDENT = 2 };
 
 struct KernelParams2 {
@@ -45,44 +45,75 @@ struct KernelParams2 {
   float out1_slope;
   int has_res, has_acc, has_out0, has_out1;
   int halo_rows;    // HALO/RESIDENT: rows of the activation box (128 + (taps-1)*tap_stride, padded to 8)
+  int ep_entries;   // epilogue ring depth (2..8)
+  int ep_bufs;      // slabs per entry: 1 (one input-or-output tensor) or 2
+  int w_bytes;      // RESIDENT: bytes of the weight area
+  int store_depth;  // TMA store groups kept in flight by the store warp (0..2)
+  int mma_pipes;    // 1: warp 1 issues every tile; 2: warps 1 and 12 issue alternate tiles (small N: issue bound)
+  long long* trace; // debug: per-role clock64 timeline of CTA 0 (jatts_debug_set_trace), else null
 };
+
+long long* g_trace_ptr = nullptr;
+#define JB_TRACE(role, ev, idx)                                                                \
+  do {                                                                                         \
+    if (P.trace && blockIdx.x == 0 && (idx) < 64) P.trace[((role) * 8 + (ev)) * 64 + (idx)] = clock64(); \
+  } while (0)
 
 template <int BLOCK_N, int KCH, int MODE>
 struct Cfg2 {
-  static constexpr int SLAB = BLOCK_N >= 64 ? 64 : 32;     // columns per epilogue slab
+  // epilogue slabs: [128 rows x 32 columns] bf16 = 64-byte rows (SWIZZLE_64B), 8 KB.  An epilogue ring
+  // entry holds 1 or 2 slabs ([residual -> out0 | branch sum -> out1]); the ring depth is whatever
+  // shared memory is left (launch2), because the per-tile critical path is latency x concurrency:
+  // residual prefetch distance and the number of TMA stores in flight both scale with it.
+  static constexpr int SLAB = 32;
   static constexpr int N_SLABS = BLOCK_N / SLAB;
-  static constexpr int ROWB = SLAB * 2;                     // bytes per slab row = swizzle span
-  static constexpr int SW_MASK = ROWB == 128 ? 7 : 3;       // Swizzle<3,4,3> / Swizzle<2,4,3>
-  static constexpr int SLAB_BYTES = BLOCK_M2 * ROWB;
-  static constexpr int ENTRY_BYTES = 2 * SLAB_BYTES;        // [residual -> out0 | branch sum -> out1]
-  static constexpr int EP_ENTRIES = MODE == MODE_RESIDENT ? (BLOCK_N == 32 ? 4 : 2)
-                                                          : (BLOCK_N == 256 ? 2 : (BLOCK_N == 32 ? 4 : 3));
+  static constexpr int ROWB = SLAB * 2;
+  static constexpr int SW_MASK = 3;                         // Swizzle<2,4,3>
+  static constexpr int SLAB_BYTES = BLOCK_M2 * ROWB;        // 8192
+  static constexpr int MAX_ENTRIES = 8;
   static constexpr int KROWB = KCH * 2;                     // operand row bytes (128 or 64) = swizzle span
   static constexpr int A_BYTES = BLOCK_M2 * KROWB;
   static constexpr int B_BYTES = BLOCK_N * KROWB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BIAS_BYTES = 2048;                   // n_pad <= 512
   static constexpr int BAR_BYTES = 1024;                    // keeps the resident weight area 1024-aligned
-  static constexpr int FIXED_TAIL = EP_ENTRIES * ENTRY_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
-  static constexpr int BUDGET = 225 * 1024 - FIXED_TAIL;
+  static constexpr int FIXED_TAIL = BIAS_BYTES + BAR_BYTES + 1024;
+  static constexpr int MIN_EP_BYTES = 4 * 2 * SLAB_BYTES;   // the mainloop leaves at least 4 two-slab entries
+  static constexpr int BUDGET = 227 * 1024 - FIXED_TAIL - MIN_EP_BYTES;
   // STREAM
   static constexpr int MAX_STAGES = BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int STAGES = MAX_STAGES >= 6 ? 6 : (MAX_STAGES >= 4 ? 4 : 2);   // even: half per pipeline
   // HALO / RESIDENT: activation slabs [HALO_MAX_ROWS x KCH]
   static constexpr int HALO_MAX_ROWS = 192;                 // 128 + (11-1)*5 = 178, padded
   static constexpr int A_SLAB_BYTES = HALO_MAX_ROWS * KROWB;  // multiple of 1024
-  static constexpr int A_STAGES = MODE == MODE_RESIDENT ? (BLOCK_N == 32 ? 4 : 2) : (BLOCK_N == 256 ? 2 : 3);
+  static constexpr int A_STAGES = (MODE == MODE_RESIDENT && BLOCK_N == 32) ? 4 : 2;   // even: half per pipeline when two MMA warps issue
   static constexpr int B_MAX = (BUDGET - A_STAGES * A_SLAB_BYTES) / B_BYTES;
-  static constexpr int B_STAGES = B_MAX > 8 ? 8 : B_MAX;
+  static constexpr int B_STAGES = B_MAX >= 4 ? 4 : 2;
   static constexpr int MAIN_BYTES = MODE == MODE_STREAM ? STAGES * STAGE_BYTES
                                   : MODE == MODE_HALO   ? A_STAGES * A_SLAB_BYTES + B_STAGES * B_BYTES
                                                         : A_STAGES * A_SLAB_BYTES;
-  static constexpr int SMEM_FIXED = MAIN_BYTES + FIXED_TAIL;   // + resident weight bytes in RESIDENT mode
+  static constexpr int SMEM_FIXED = MAIN_BYTES + FIXED_TAIL;   // + epilogue ring + resident weights (launch2)
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static_assert(MODE != MODE_STREAM || STAGES >= 2, "stream pipeline depth");
-  static_assert(MODE != MODE_HALO || B_STAGES >= 2, "weight ring depth");
+  static_assert(MODE != MODE_STREAM || MAX_STAGES >= 2, "stream pipeline depth");
+  static_assert(MODE != MODE_HALO || B_MAX >= 2, "weight ring depth");
   static_assert(A_STAGES <= 4 && STAGES <= 8 && B_STAGES <= 8, "barrier arrays");
 };
+
+// Ring position of item `inner` (0..per_tile-1) of the tile with sequence number `seq`.  Tiles alternate
+// between two independent pipelines (even / odd seq); each pipeline owns half of every ring so that every
+// mbarrier has exactly one producer and one consumer walking it in lockstep (an mbarrier parity wait
+// cannot tell "two phases ahead" from "done", so a consumer must never share a barrier with a faster one).
+struct RingPos { int idx; uint32_t phase; };
+__device__ __forceinline__ RingPos ring_pos(int seq, int inner, int per_tile, int depth, int npipe = 2) {
+  // npipe == 1: one consumer walks the whole ring; npipe == 2: each pipeline owns depth/2 slots
+  const int pipe = npipe == 2 ? (seq & 1) : 0;
+  const int depth_per_pipe = npipe == 2 ? depth >> 1 : depth;
+  const uint32_t cnt = static_cast<uint32_t>(npipe == 2 ? seq >> 1 : seq) * per_tile + inner;
+  RingPos r;
+  r.idx = pipe * depth_per_pipe + static_cast<int>(cnt % depth_per_pipe);
+  r.phase = (cnt / depth_per_pipe) & 1u;
+  return r;
+}
 
 // K-major operand tile with rows of exactly one swizzle span (128 B: KCH = 64, 64 B: KCH = 32)
 template <int KCH>
@@ -104,15 +135,16 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                      const __grid_constant__ KernelParams2 P) {
   using C = Cfg2<BLOCK_N, KCH, MODE>;
   constexpr int STAGES = C::STAGES;
-  constexpr int E = C::EP_ENTRIES;
   constexpr int KSTEPS = KCH / UMMA_K2;
+  const int E = P.ep_entries;
+  const int entry_bytes = P.ep_bufs * C::SLAB_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_base = smem + C::A_STAGES * C::A_SLAB_BYTES;             // HALO: weight ring after the A slabs
-  uint8_t* ep_base = smem + C::MAIN_BYTES;                            // 1024-aligned (all sizes are multiples)
-  float* bias_s = reinterpret_cast<float*>(ep_base + E * C::ENTRY_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem + C::MAIN_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + C::BIAS_BYTES);
   uint8_t* w_base = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;  // RESIDENT: all weight tiles (1024-aligned)
+  uint8_t* ep_base = w_base + P.w_bytes;                              // epilogue ring (1024-aligned)
   constexpr int NB = 8;
   uint64_t* full_bar = bars;                    // [NB]   STREAM: A+B stage | HALO: weight ring
   uint64_t* empty_bar = full_bar + NB;          // [NB]
@@ -120,10 +152,11 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   uint64_t* aempty_bar = afull_bar + 4;         // [4]
   uint64_t* tfull_bar = aempty_bar + 4;         // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
-  uint64_t* epfull_bar = tempty_bar + 2;        // [E]
-  uint64_t* epempty_bar = epfull_bar + E;       // [E]
-  uint64_t* ready_bar = epempty_bar + E;        // [E]    epilogue -> store warp: slab written
-  uint64_t* wfull_bar = ready_bar + E;          // [1]    RESIDENT: weights landed
+  constexpr int ME = C::MAX_ENTRIES;
+  uint64_t* epfull_bar = tempty_bar + 2;        // [ME]
+  uint64_t* epempty_bar = epfull_bar + ME;      // [ME]
+  uint64_t* ready_bar = epempty_bar + ME;       // [ME]   epilogue -> store warp: slab written
+  uint64_t* wfull_bar = ready_bar + ME;         // [1]    RESIDENT: weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -149,7 +182,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
     }
-    for (int i = 0; i < E; ++i) {
+    for (int i = 0; i < ME; ++i) {
       mbar_init(&epfull_bar[i], 1);
       mbar_init(&epempty_bar[i], 1);
       mbar_init(&ready_bar[i], 128);
@@ -172,72 +205,80 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   if (warp == 0) {
     // ===================== mainloop TMA producer =====================
     if (elect_one()) {
-      if (MODE == MODE_STREAM) {
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
-          const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+      if (MODE == MODE_RESIDENT) {
+        // every weight tile of this convolution, once per CTA (num_n_tiles == 1 in this mode)
+        mbar_expect_tx(wfull_bar, static_cast<uint32_t>(P.taps * P.k_chunks) * C::B_BYTES);
+        for (int kc = 0; kc < P.k_chunks; ++kc)
+          for (int tap = 0; tap < P.taps; ++tap)
+            tma_load_2d(&tm_b, wfull_bar, w_base + (kc * P.taps + tap) * C::B_BYTES, kc * KCH, tap * P.n_pad);
+      }
+      const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * C::KROWB;
+      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+        const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
+        const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+        if (MODE == MODE_STREAM) {
+          const int k_iters = P.taps * P.k_chunks;
+          int it = 0;
           for (int tap = 0; tap < P.taps; ++tap) {
             const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
             const int brow = tap * P.n_pad + n0;
-            for (int kc = 0; kc < P.k_chunks; ++kc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* s = smem + stage * C::STAGE_BYTES;
-              mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-              tma_load_2d(&tm_a, &full_bar[stage], s, kc * KCH, arow);
-              tma_load_2d(&tm_b, &full_bar[stage], s + C::A_BYTES, kc * KCH, brow);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int kc = 0; kc < P.k_chunks; ++kc, ++it) {
+              const RingPos rp = ring_pos(seq, it, k_iters, STAGES, P.mma_pipes);
+              mbar_wait(&empty_bar[rp.idx], rp.phase ^ 1);
+              uint8_t* st = smem + rp.idx * C::STAGE_BYTES;
+              mbar_expect_tx(&full_bar[rp.idx], C::STAGE_BYTES);
+              tma_load_2d(&tm_a, &full_bar[rp.idx], st, kc * KCH, arow);
+              tma_load_2d(&tm_b, &full_bar[rp.idx], st + C::A_BYTES, kc * KCH, brow);
             }
           }
-        }
-      } else {
-        if (MODE == MODE_RESIDENT) {
-          // every weight tile of this convolution, once per CTA (num_n_tiles == 1 in this mode)
-          mbar_expect_tx(wfull_bar, static_cast<uint32_t>(P.taps * P.k_chunks) * C::B_BYTES);
-          for (int kc = 0; kc < P.k_chunks; ++kc)
-            for (int tap = 0; tap < P.taps; ++tap)
-              tma_load_2d(&tm_b, wfull_bar, w_base + (kc * P.taps + tap) * C::B_BYTES, kc * KCH, tap * P.n_pad);
-        }
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
-        const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * C::KROWB;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
-          const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+        } else {
           for (int kc = 0; kc < P.k_chunks; ++kc) {
-            mbar_wait(&aempty_bar[as], aph ^ 1);
-            mbar_expect_tx(&afull_bar[as], a_bytes);
-            tma_load_2d(&tm_a, &afull_bar[as], smem + as * C::A_SLAB_BYTES, kc * KCH, m0 + P.tap_off0);
-            if (++as == C::A_STAGES) { as = 0; aph ^= 1; }
+            const RingPos ra = ring_pos(seq, kc, P.k_chunks, C::A_STAGES, P.mma_pipes);
+            mbar_wait(&aempty_bar[ra.idx], ra.phase ^ 1);
+            if (kc == 0) JB_TRACE(0, 0, seq);
+            mbar_expect_tx(&afull_bar[ra.idx], a_bytes);
+            tma_load_2d(&tm_a, &afull_bar[ra.idx], smem + ra.idx * C::A_SLAB_BYTES, kc * KCH, m0 + P.tap_off0);
             if (MODE == MODE_HALO) {
               for (int tap = 0; tap < P.taps; ++tap) {
-                mbar_wait(&empty_bar[bs], bph ^ 1);
-                mbar_expect_tx(&full_bar[bs], C::B_BYTES);
-                tma_load_2d(&tm_b, &full_bar[bs], b_base + bs * C::B_BYTES, kc * KCH, tap * P.n_pad + n0);
-                if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+                const RingPos rb = ring_pos(seq, kc * P.taps + tap, P.k_chunks * P.taps, C::B_STAGES, P.mma_pipes);
+                mbar_wait(&empty_bar[rb.idx], rb.phase ^ 1);
+                mbar_expect_tx(&full_bar[rb.idx], C::B_BYTES);
+                tma_load_2d(&tm_b, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES, kc * KCH, tap * P.n_pad + n0);
               }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 12) {
+    // ===================== MMA issuers (two pipelines: even / odd tiles) =====================
+    // Measured (tools_gpu_trace.py): for N <= 64 a single issuing thread is the bottleneck -- ~57 clk to
+    // issue one tcgen05.mma that executes in 16-32 clk, plus ~450 clk per mbarrier wait.  Two warps issue
+    // alternate tiles into their own TMEM accumulator; ring positions are computed from the tile sequence
+    // number so both consumers walk the same rings without talking to each other.
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if (MODE == MODE_STREAM) {
-        const int k_iters = P.taps * P.k_chunks;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      const int pipe = warp == 1 ? 0 : 1;
+      const uint32_t w_addr = smem_u32(w_base);
+      bool weights_ready = MODE != MODE_RESIDENT;
+      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+        if (P.mma_pipes == 2 ? (seq & 1) != pipe : pipe != 0) continue;
+        const int acc = seq & 1;   // accumulator (and epilogue group) of this tile
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        mbar_wait(&tempty_bar[acc], ((seq >> 1) & 1) ^ 1);
+        if (pipe == 0) JB_TRACE(1, 0, seq);
+        tc_fence_after();
+        if (!weights_ready) {
+          mbar_wait(wfull_bar, 0);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+          weights_ready = true;
+        }
+        if (MODE == MODE_STREAM) {
+          const int k_iters = P.taps * P.k_chunks;
           for (int it = 0; it < k_iters; ++it) {
-            mbar_wait(&full_bar[stage], phase);
+            const RingPos rp = ring_pos(seq, it, k_iters, STAGES, P.mma_pipes);
+            const int stage = rp.idx;
+            mbar_wait(&full_bar[stage], rp.phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint64_t da = make_kmajor_desc<KCH>(sa);
@@ -248,31 +289,22 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
               tc_mma_bf16(tmem_d, da + koff, db + koff, idesc, (it | k) != 0 ? 1u : 0u);
             }
             tc_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&tfull_bar[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-      } else {
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
-        if (MODE == MODE_RESIDENT) {
-          mbar_wait(wfull_bar, 0);
-          tc_fence_after();
-        }
-        const uint32_t w_addr = smem_u32(w_base);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        } else {
           for (int kc = 0; kc < P.k_chunks; ++kc) {
-            mbar_wait(&afull_bar[as], aph);
+            const RingPos ra = ring_pos(seq, kc, P.k_chunks, C::A_STAGES, P.mma_pipes);
+            const int as = ra.idx;
+            mbar_wait(&afull_bar[as], ra.phase);
+            if (pipe == 0 && kc == 0) JB_TRACE(1, 1, seq);
             tc_fence_after();
             const uint32_t slab = smem_u32(smem + as * C::A_SLAB_BYTES);
             for (int tap = 0; tap < P.taps; ++tap) {
               uint32_t b_addr;
+              int bs = 0;
               if (MODE == MODE_HALO) {
-                mbar_wait(&full_bar[bs], bph);
+                const RingPos rb = ring_pos(seq, kc * P.taps + tap, P.k_chunks * P.taps, C::B_STAGES, P.mma_pipes);
+                bs = rb.idx;
+                mbar_wait(&full_bar[bs], rb.phase);
                 tc_fence_after();
                 b_addr = smem_u32(b_base + bs * C::B_BYTES);
               } else {
@@ -289,114 +321,140 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                 const uint64_t koff = static_cast<uint64_t>((k * UMMA_K2 * 2) >> 4);
                 tc_mma_bf16(tmem_d, da + koff, db + koff, idesc, (kc | tap | k) != 0 ? 1u : 0u);
               }
-              if (MODE == MODE_HALO) {
-                tc_commit(&empty_bar[bs]);
-                if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
-              }
+              if (MODE == MODE_HALO) tc_commit(&empty_bar[bs]);
             }
             tc_commit(&aempty_bar[as]);
-            if (++as == C::A_STAGES) { as = 0; aph ^= 1; }
           }
-          tc_commit(&tfull_bar[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        tc_commit(&tfull_bar[acc]);
+        if (pipe == 0) JB_TRACE(1, 2, seq);
       }
     }
   } else if (warp == 2) {
     // ===================== epilogue loader =====================
     if (elect_one()) {
-      int e = 0;
-      uint32_t ph = 0;
       const uint32_t bytes = (P.has_res ? C::SLAB_BYTES : 0) + (P.has_acc ? C::SLAB_BYTES : 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
         const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
         const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
         for (int s = 0; s < C::N_SLABS; ++s) {
-          mbar_wait(&epempty_bar[e], ph ^ 1);
-          uint8_t* buf = ep_base + e * C::ENTRY_BYTES;
+          const RingPos re = ring_pos(seq, s, C::N_SLABS, E);
+          const int e = re.idx;
+          mbar_wait(&epempty_bar[e], re.phase ^ 1);
+          if (s == 0) JB_TRACE(2, 0, seq);
+          uint8_t* buf = ep_base + e * entry_bytes;
           if (bytes) {
             mbar_expect_tx(&epfull_bar[e], bytes);
             if (P.has_res) tma_load_2d(&tm_res, &epfull_bar[e], buf, n0 + s * C::SLAB, m0);
-            if (P.has_acc) tma_load_2d(&tm_acc, &epfull_bar[e], buf + C::SLAB_BYTES, n0 + s * C::SLAB, m0);
+            if (P.has_acc) tma_load_2d(&tm_acc, &epfull_bar[e], buf + (P.ep_bufs - 1) * C::SLAB_BYTES, n0 + s * C::SLAB, m0);
           } else {
             mbar_arrive(&epfull_bar[e]);
           }
-          if (++e == E) { e = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 3) {
     // ===================== store warp: slab -> global by TMA =====================
     if (elect_one()) {
-      int e = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int groups = 0;
+      int hist0 = 0, hist1 = 0;   // entries of the two most recently committed store groups
+      const int depth = P.store_depth;   // older groups kept in flight behind the one just committed (0..2)
+      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
         const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
         const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
         for (int s = 0; s < C::N_SLABS; ++s) {
-          mbar_wait(&ready_bar[e], ph);      // all 128 epilogue threads wrote + fenced this slab
-          uint8_t* bufA = ep_base + e * C::ENTRY_BYTES;
+          const RingPos re = ring_pos(seq, s, C::N_SLABS, E);
+          const int e = re.idx;
+          mbar_wait(&ready_bar[e], re.phase);  // the 128 threads of the tile's epilogue group wrote + fenced this slab
+          if (s == 0) JB_TRACE(3, 0, seq);
+          uint8_t* bufA = ep_base + e * entry_bytes;
           if (P.has_out0) tma_store_2d(&tm_out0, bufA, n0 + s * C::SLAB, m0);
-          if (P.has_out1) tma_store_2d(&tm_out1, bufA + C::SLAB_BYTES, n0 + s * C::SLAB, m0);
+          if (P.has_out1) tma_store_2d(&tm_out1, bufA + (P.ep_bufs - 1) * C::SLAB_BYTES, n0 + s * C::SLAB, m0);
           tma_store_commit();
-          tma_store_wait_read<0>();          // smem has been read: the entry can be refilled
-          mbar_arrive(&epempty_bar[e]);
-          if (++e == E) { e = 0; ph ^= 1; }
+          ++groups;
+          // `depth` older store groups stay in flight; the entry of the group that has certainly finished
+          // reading its slab goes back to the loader
+          int release;
+          if (depth == 0) { tma_store_wait_read<0>(); release = e; }
+          else if (depth == 1) { tma_store_wait_read<1>(); release = hist0; }
+          else { tma_store_wait_read<2>(); release = hist1; }
+          if (groups > depth) mbar_arrive(&epempty_bar[release]);
+          hist1 = hist0;
+          hist0 = e;
+          if (s == 0) JB_TRACE(3, 1, seq);
         }
       }
+      // (entries still held at the end are never needed again)
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue (warps 4..7) =====================
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== epilogue (warps 4..7: even tiles, warps 8..11: odd tiles) =====================
+    constexpr int CW = C::SLAB;               // one warp handles its 32 rows x the whole 32-column slab
     const int lane_group = warp & 3;
+    const int pipe = (warp - 4) >> 2;
+    const int half = 0;
+    const float act_slope = P.act == ACT_LRELU ? P.slope : 1.0f;
     const int row_in_tile = lane_group * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
     const uint32_t row_off = static_cast<uint32_t>(row_in_tile * C::ROWB);
     const uint32_t sw = (row_off >> 7) & C::SW_MASK;   // XOR pattern of this row's 16-byte chunks
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int e = 0;
-    uint32_t ph = 0;
-    // row validity of the NEXT tile is fetched while the current one is processed (one global byte per
-    // thread per tile; its latency used to sit on the per-tile critical path)
-    auto row_valid = [&](int tile) -> bool {
-      if (tile >= num_tiles) return false;
+    const int acc = pipe;
+    uint32_t n_done = 0;
+    // row validity of this group's NEXT tile is fetched while the current one is processed; the raw byte
+    // stays in a register and is only compared one tile later, so the load is off the critical path
+    auto row_valid = [&](int tile) -> unsigned {
+      if (tile >= num_tiles) return 0u;
       const int row = (tile / P.num_n_tiles) * BLOCK_M2 + row_in_tile;
-      if (row >= P.m_rows) return false;
-      return P.frame_mask ? P.frame_mask[row / P.rate] != 0 : true;
+      if (row >= P.m_rows) return 0u;
+      return P.frame_mask ? static_cast<unsigned>(__ldg(P.frame_mask + row / P.rate)) : 1u;
     };
-    bool valid_next = row_valid(blockIdx.x);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    unsigned valid_next = row_valid(blockIdx.x + pipe * gridDim.x);
+    for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+      if ((seq & 1) != pipe) continue;
       const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
-      const bool valid = valid_next;
-      valid_next = row_valid(tile + gridDim.x);
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      const float row_scale = valid_next != 0u ? P.post_scale : 0.0f;
+      valid_next = row_valid(tile + 2 * gridDim.x);
+      if (warp == 4 && lane == 0) JB_TRACE(4, 3, seq);
+      mbar_wait(&tfull_bar[acc], n_done & 1);
+      ++n_done;
+      if (warp == 4 && lane == 0) JB_TRACE(4, 0, seq);
       tc_fence_after();
 #pragma unroll 1
       for (int s = 0; s < C::N_SLABS; ++s) {
-        uint32_t r[C::SLAB];
+        // each of the two warps of a TMEM lane group owns half of the slab's columns
+        uint32_t r[CW];
         {
-          uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-          tmem_ld32(lane_addr + static_cast<uint32_t>(acc * BLOCK_N + s * C::SLAB), r0);
-          if (C::SLAB == 64) {
-            uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[C::SLAB == 64 ? 32 : 0]);
-            tmem_ld32(lane_addr + static_cast<uint32_t>(acc * BLOCK_N + s * C::SLAB + 32), r1);
+          const uint32_t ta = lane_addr + static_cast<uint32_t>(acc * BLOCK_N + s * C::SLAB + half * CW);
+          if (CW == 32) {
+            uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+            tmem_ld32(ta, r0);
+          } else {
+            uint32_t(&r0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[0]);
+            tmem_ld16(ta, r0);
           }
         }
-        mbar_wait(&epfull_bar[e], ph);       // residual / branch-sum slabs have landed (or entry is free)
+        const RingPos re = ring_pos(seq, s, C::N_SLABS, E);
+        const int e = re.idx;
+        mbar_wait(&epfull_bar[e], re.phase);   // residual / branch-sum slabs have landed (or entry is free)
+        if (s == 0 && warp == 4 && lane == 0) JB_TRACE(4, 1, seq);
         tmem_ld_wait();
-        uint8_t* bufA = ep_base + e * C::ENTRY_BYTES;
-        uint8_t* bufB = bufA + C::SLAB_BYTES;
-        const float* bs = bias_s + n0 + s * C::SLAB;
+        if (s == C::N_SLABS - 1) {
+          // every TMEM read of this accumulator has completed: hand it back to the MMA warp right away
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        uint8_t* bufA = ep_base + e * entry_bytes;
+        uint8_t* bufB = bufA + (P.ep_bufs - 1) * C::SLAB_BYTES;   // == bufA when an entry is a single slab
+        const float* bs = bias_s + n0 + s * C::SLAB + half * CW;
 #pragma unroll
-        for (int c = 0; c < C::SLAB / 8; ++c) {
-          const uint32_t off = row_off + ((static_cast<uint32_t>(c) ^ sw) << 4);
+        for (int c = 0; c < CW / 8; ++c) {
+          const uint32_t off = row_off + ((static_cast<uint32_t>(half * (CW / 8) + c) ^ sw) << 4);
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float x = __uint_as_float(r[c * 8 + i]) + bs[c * 8 + i];
-            if (P.act == ACT_LRELU) x = x > 0.f ? x : x * P.slope;
-            v[i] = x;
+            const float x = __uint_as_float(r[c * 8 + i]) + bs[c * 8 + i];
+            v[i] = fmaxf(x, x * act_slope);   // LeakyReLU (slope in (0,1)); act_slope == 1 -> identity
           }
           if (P.has_res) {
             const uint4 t = *reinterpret_cast<const uint4*>(bufA + off);
@@ -417,7 +475,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = valid ? v[i] * P.post_scale : 0.f;
+          for (int i = 0; i < 8; ++i) v[i] *= row_scale;   // post_scale, or 0 for rows outside every utterance
           if (P.has_out0) {
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -427,24 +485,17 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           if (P.has_out1) {
             const float sl = P.out1_slope;
             uint4 o;
-            o.x = pack_bf16x2(v[0] > 0.f ? v[0] : v[0] * sl, v[1] > 0.f ? v[1] : v[1] * sl);
-            o.y = pack_bf16x2(v[2] > 0.f ? v[2] : v[2] * sl, v[3] > 0.f ? v[3] : v[3] * sl);
-            o.z = pack_bf16x2(v[4] > 0.f ? v[4] : v[4] * sl, v[5] > 0.f ? v[5] : v[5] * sl);
-            o.w = pack_bf16x2(v[6] > 0.f ? v[6] : v[6] * sl, v[7] > 0.f ? v[7] : v[7] * sl);
+            o.x = pack_bf16x2(fmaxf(v[0], v[0] * sl), fmaxf(v[1], v[1] * sl));
+            o.y = pack_bf16x2(fmaxf(v[2], v[2] * sl), fmaxf(v[3], v[3] * sl));
+            o.z = pack_bf16x2(fmaxf(v[4], v[4] * sl), fmaxf(v[5], v[5] * sl));
+            o.w = pack_bf16x2(fmaxf(v[6], v[6] * sl), fmaxf(v[7], v[7] * sl));
             *reinterpret_cast<uint4*>(bufB + off) = o;
           }
         }
-        if (s == C::N_SLABS - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
         fence_proxy_async_smem();            // make the generic-proxy smem writes visible to the TMA engine
         mbar_arrive(&ready_bar[e]);          // hand the slab to the store warp; nobody waits here
-        if (++e == E) { e = 0; ph ^= 1; }
+        if (s == 0 && warp == 4 && lane == 0) JB_TRACE(4, 2, seq);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -515,9 +566,24 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.has_out0 = e.out_hi != nullptr;
   kp.has_out1 = e.out_act != nullptr;
   kp.halo_rows = halo_rows;
-  const int w_bytes = MODE == MODE_RESIDENT ? p.taps * k_chunks * C::B_BYTES : 0;
-  const int smem_bytes = C::SMEM_FIXED + w_bytes;
-  JB_REQUIRE(smem_bytes <= 227 * 1024, -2, "conv_gemm_tc2: shared memory budget exceeded");
+  const int w_bytes = MODE == MODE_RESIDENT ? round_up(p.taps * k_chunks * C::B_BYTES, 1024) : 0;
+  // epilogue ring: every byte the mainloop leaves, up to 8 entries
+  kp.ep_bufs = (kp.has_res + kp.has_acc > 1 || kp.has_out0 + kp.has_out1 > 1) ? 2 : 1;
+  const int entry = kp.ep_bufs * C::SLAB_BYTES;
+  int entries = (227 * 1024 - C::SMEM_FIXED - w_bytes) / entry;
+  if (entries > C::MAX_ENTRIES) entries = C::MAX_ENTRIES;
+  entries &= ~1;   // half of the ring per pipeline
+  JB_REQUIRE(entries >= 2, -2, "conv_gemm_tc2: shared memory budget exceeded");
+  kp.ep_entries = entries;
+  kp.w_bytes = w_bytes;
+  kp.trace = g_trace_ptr;
+  static const char* mp_env = getenv("JATTS_B200_MMA_PIPES");
+  // measured: two issuing warps contend for the tensor-core issue port (84 vs 57 clk per MMA) -- one is better
+  kp.mma_pipes = (mp_env && atoi(mp_env) == 2) ? 2 : 1;
+  kp.store_depth = entries >= 6 ? 2 : (entries >= 4 ? 1 : 0);
+  static const char* sd_env = getenv("JATTS_B200_STORE_DEPTH");
+  if (sd_env) kp.store_depth = atoi(sd_env) < entries - 1 ? atoi(sd_env) : entries - 2;
+  const int smem_bytes = C::SMEM_FIXED + w_bytes + entries * entry;
   auto kern = conv_bf16_tma_kernel<BLOCK_N, KCH, MODE>;
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
@@ -550,7 +616,7 @@ int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream) {
   // RESIDENT when every weight tile of the convolution fits next to the pipeline buffers
   auto resident_ok = [&](int fixed, int b_bytes, int kch) {
     return halo_ok && max_mode >= MODE_RESIDENT && p.n_pad == p.block_n &&
-           fixed + p.taps * ceil_div(a_cols, kch) * b_bytes <= 227 * 1024;
+           fixed + round_up(p.taps * ceil_div(a_cols, kch) * b_bytes, 1024) + 4 * 2 * 8192 <= 227 * 1024;
   };
   switch (p.block_n) {
     case 32:
