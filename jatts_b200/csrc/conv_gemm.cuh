@@ -55,6 +55,14 @@ struct ConvGemmProblem {
   // transposed-conv (polyphase) row remap: 0 => plain.  out_row = row*up_s + (n / up_cout) - up_p,
   // out_col = n % up_cout
   int up_s, up_p, up_cout;
+  // One PHASE of a polyphase transposed convolution expressed as a plain 2-tap convolution for the
+  // TMA-epilogue kernel (all zero = not used): weight rows of tap t start at w_row0 + t*w_tap_stride,
+  // output row of GEMM row r is (r + store_row_off) in an output view whose row pitch is out_pitch_mul
+  // times the tensor's (the caller offsets the out pointers to the view's first row and gives its row
+  // count in out_view_rows), and row validity is frame_mask[(r*mask_mul + mask_add) / rate].
+  int w_row0, w_tap_stride, w_rows_total;
+  int store_row_off, out_pitch_mul, out_view_rows;
+  int mask_mul, mask_add;
   ConvGemmEpilogue ep;
 };
 

@@ -49,6 +49,9 @@ struct KernelParams2 {
   int ep_bufs;      // slabs per entry: 1 (one input-or-output tensor) or 2
   int w_bytes;      // RESIDENT: bytes of the weight area
   int store_depth;  // TMA store groups kept in flight by the store warp (0..2)
+  int w_row0, w_tap_stride;       // weight rows of tap t: w_row0 + t*w_tap_stride (+ n0)
+  int store_row_off;              // output row coordinate = m0 + store_row_off
+  int mask_mul, mask_add, out_rows;  // validity: frame_mask[(row*mask_mul + mask_add) / rate], 0 <= . < out_rows
   int mma_pipes;    // 1: warp 1 issues every tile; 2: warps 1 and 12 issue alternate tiles (small N: issue bound)
   long long* trace; // debug: per-role clock64 timeline of CTA 0 (jatts_debug_set_trace), else null
 };
@@ -210,7 +213,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         mbar_expect_tx(wfull_bar, static_cast<uint32_t>(P.taps * P.k_chunks) * C::B_BYTES);
         for (int kc = 0; kc < P.k_chunks; ++kc)
           for (int tap = 0; tap < P.taps; ++tap)
-            tma_load_2d(&tm_b, wfull_bar, w_base + (kc * P.taps + tap) * C::B_BYTES, kc * KCH, tap * P.n_pad);
+            tma_load_2d(&tm_b, wfull_bar, w_base + (kc * P.taps + tap) * C::B_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride);
       }
       const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * C::KROWB;
       for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
@@ -221,7 +224,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           int it = 0;
           for (int tap = 0; tap < P.taps; ++tap) {
             const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
-            const int brow = tap * P.n_pad + n0;
+            const int brow = P.w_row0 + tap * P.w_tap_stride + n0;
             for (int kc = 0; kc < P.k_chunks; ++kc, ++it) {
               const RingPos rp = ring_pos(seq, it, k_iters, STAGES, P.mma_pipes);
               mbar_wait(&empty_bar[rp.idx], rp.phase ^ 1);
@@ -243,7 +246,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                 const RingPos rb = ring_pos(seq, kc * P.taps + tap, P.k_chunks * P.taps, C::B_STAGES, P.mma_pipes);
                 mbar_wait(&empty_bar[rb.idx], rb.phase ^ 1);
                 mbar_expect_tx(&full_bar[rb.idx], C::B_BYTES);
-                tma_load_2d(&tm_b, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES, kc * KCH, tap * P.n_pad + n0);
+                tma_load_2d(&tm_b, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride + n0);
               }
             }
           }
@@ -368,8 +371,8 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           mbar_wait(&ready_bar[e], re.phase);  // the 128 threads of the tile's epilogue group wrote + fenced this slab
           if (s == 0) JB_TRACE(3, 0, seq);
           uint8_t* bufA = ep_base + e * entry_bytes;
-          if (P.has_out0) tma_store_2d(&tm_out0, bufA, n0 + s * C::SLAB, m0);
-          if (P.has_out1) tma_store_2d(&tm_out1, bufA + (P.ep_bufs - 1) * C::SLAB_BYTES, n0 + s * C::SLAB, m0);
+          if (P.has_out0) tma_store_2d(&tm_out0, bufA, n0 + s * C::SLAB, m0 + P.store_row_off);
+          if (P.has_out1) tma_store_2d(&tm_out1, bufA + (P.ep_bufs - 1) * C::SLAB_BYTES, n0 + s * C::SLAB, m0 + P.store_row_off);
           tma_store_commit();
           ++groups;
           // `depth` older store groups stay in flight; the entry of the group that has certainly finished
@@ -406,7 +409,9 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       if (tile >= num_tiles) return 0u;
       const int row = (tile / P.num_n_tiles) * BLOCK_M2 + row_in_tile;
       if (row >= P.m_rows) return 0u;
-      return P.frame_mask ? static_cast<unsigned>(__ldg(P.frame_mask + row / P.rate)) : 1u;
+      const long long orow = static_cast<long long>(row) * P.mask_mul + P.mask_add;
+      if (orow < 0 || orow >= P.out_rows) return 0u;
+      return P.frame_mask ? static_cast<unsigned>(__ldg(P.frame_mask + orow / P.rate)) : 1u;
     };
     unsigned valid_next = row_valid(blockIdx.x + pipe * gridDim.x);
     for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
@@ -518,8 +523,9 @@ bool conv_gemm_tc2_eligible(const ConvGemmProblem& p) {
   if (!(e.act == ACT_NONE || e.act == ACT_LRELU)) return false;
   if (e.res_f32 || e.accum_in || e.out_f32 || e.out_lo) return false;
   if (e.scale != 1.0f) return false;
-  if (p.n != p.n_pad || p.n_pad > 512) return false;
-  if (p.out_rows != p.m_rows) return false;
+  const bool phase = p.w_tap_stride != 0;
+  if ((!phase && p.n != p.n_pad) || p.n > 512 || p.n % p.block_n != 0) return false;
+  if (!phase && p.out_rows != p.m_rows) return false;
   const int slab = p.block_n >= 64 ? 64 : 32;
   auto ok = [&](const void* ptr, int ld) { return ptr == nullptr || (ld % 8 == 0 && ld >= p.n && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0); };
   if (!ok(e.res_bf16, e.res_ld) || !ok(e.accum_bf16, e.res_ld) || !ok(e.out_hi, e.out_bf_ld) || !ok(e.out_act, e.out_act_ld))
@@ -539,21 +545,24 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   const int k_chunks = ceil_div(a_cols, KCH);   // channel padding beyond a_cols is all-zero: skip it
   const int halo_rows = round_up(BLOCK_M2 + (p.taps - 1) * p.tap_stride, 8);
   JB_PROPAGATE(make_tmap(&ta, p.a_hi, p.a_rows, a_cols, p.a_ld, MODE == MODE_STREAM ? BLOCK_M2 : halo_rows, KCH));
-  JB_PROPAGATE(make_tmap(&tb, p.w_hi, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BLOCK_N, KCH));
+  const long long w_rows = p.w_tap_stride != 0 ? static_cast<long long>(p.w_rows_total) : static_cast<long long>(p.taps) * p.n_pad;
+  JB_PROPAGATE(make_tmap(&tb, p.w_hi, w_rows, p.k_pad, p.k_pad, BLOCK_N, KCH));
   tres = tacc = to0 = to1 = ta;
   if (e.res_bf16) JB_PROPAGATE(make_tmap(&tres, e.res_bf16, p.m_rows, p.n, e.res_ld, BLOCK_M2, C::SLAB));
   if (e.accum_bf16) JB_PROPAGATE(make_tmap(&tacc, e.accum_bf16, p.m_rows, p.n, e.res_ld, BLOCK_M2, C::SLAB));
-  if (e.out_hi) JB_PROPAGATE(make_tmap(&to0, e.out_hi, p.m_rows, p.n, e.out_bf_ld, BLOCK_M2, C::SLAB));
-  if (e.out_act) JB_PROPAGATE(make_tmap(&to1, e.out_act, p.m_rows, p.n, e.out_act_ld, BLOCK_M2, C::SLAB));
+  const int pitch_mul = p.out_pitch_mul > 0 ? p.out_pitch_mul : 1;
+  const long long view_rows = p.out_pitch_mul > 0 ? p.out_view_rows : p.m_rows;
+  if (e.out_hi) JB_PROPAGATE(make_tmap(&to0, e.out_hi, view_rows, p.n, e.out_bf_ld * pitch_mul, BLOCK_M2, C::SLAB));
+  if (e.out_act) JB_PROPAGATE(make_tmap(&to1, e.out_act, view_rows, p.n, e.out_act_ld * pitch_mul, BLOCK_M2, C::SLAB));
   KernelParams2 kp;
   kp.taps = p.taps;
   kp.k_chunks = k_chunks;
-  kp.n_pad = p.n_pad;
+  kp.n_pad = p.w_tap_stride != 0 ? p.n : p.n_pad;   // bias entries / columns per tile row
   kp.tap_off0 = p.tap_off0;
   kp.tap_stride = p.tap_stride;
   kp.m_rows = p.m_rows;
   kp.num_m_tiles = ceil_div(p.m_rows, BLOCK_M2);
-  kp.num_n_tiles = p.n_pad / BLOCK_N;
+  kp.num_n_tiles = (p.w_tap_stride != 0 ? p.n : p.n_pad) / BLOCK_N;
   kp.frame_mask = p.frame_mask;
   kp.rate = p.rate > 0 ? p.rate : 1;
   kp.bias = e.bias;
@@ -566,6 +575,12 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.has_out0 = e.out_hi != nullptr;
   kp.has_out1 = e.out_act != nullptr;
   kp.halo_rows = halo_rows;
+  kp.w_row0 = p.w_row0;
+  kp.w_tap_stride = p.w_tap_stride != 0 ? p.w_tap_stride : p.n_pad;
+  kp.store_row_off = p.store_row_off;
+  kp.mask_mul = p.mask_mul > 0 ? p.mask_mul : 1;
+  kp.mask_add = p.mask_add;
+  kp.out_rows = p.out_rows;
   const int w_bytes = MODE == MODE_RESIDENT ? round_up(p.taps * k_chunks * C::B_BYTES, 1024) : 0;
   // epilogue ring: every byte the mainloop leaves, up to 8 entries
   kp.ep_bufs = (kp.has_res + kp.has_acc > 1 || kp.has_out0 + kp.has_out1 > 1) ? 2 : 1;
@@ -615,7 +630,7 @@ int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream) {
                        round_up(BLOCK_M2 + (p.taps - 1) * p.tap_stride, 8) <= 192;
   // RESIDENT when every weight tile of the convolution fits next to the pipeline buffers
   auto resident_ok = [&](int fixed, int b_bytes, int kch) {
-    return halo_ok && max_mode >= MODE_RESIDENT && p.n_pad == p.block_n &&
+    return halo_ok && max_mode >= MODE_RESIDENT && (p.w_tap_stride != 0 ? p.n : p.n_pad) == p.block_n &&
            fixed + round_up(p.taps * ceil_div(a_cols, kch) * b_bytes, 1024) + 4 * 2 * 8192 <= 227 * 1024;
   };
   switch (p.block_n) {

@@ -213,19 +213,35 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
     bf16* operands[] = {h->xa0, h->xa, h->t, h->y[nxt]};
     for (bf16* b : operands) JB_PROPAGATE(zero_gap_rows(b, co * 2, L, io.rate, s));
     {
-      // ConvTranspose1d as a 2-tap polyphase GEMM: tap 0 reads x[j], tap 1 reads x[j-1]
+      // ConvTranspose1d(k = 2s, stride s, padding p): out[j*s + q - p] = x[j] W[:,:,q] + x[j-1] W[:,:,q+s]
+      // (SURVEY appendix C).  Each output phase q is a plain 2-tap convolution over the INPUT rows whose
+      // result lands on every s-th output row, so it runs on the TMA-epilogue kernel with a strided
+      // output view: s launches, activation slab loaded once per tile, both taps' weights resident.
       const ConvW& w = h->ups[i];
-      ConvGemmProblem p{};
-      p.a_hi = h->y[cur]; p.a_rows = static_cast<int>(in_io.rows); p.a_ld = c_in; p.a_cols = c_in;
-      p.w_hi = w.hi; p.taps = 2; p.n_pad = w.n_pad; p.k_pad = w.k_pad; p.tap_off0 = 0; p.tap_stride = -1;
-      p.n = w.n; p.m_rows = static_cast<int>(in_io.rows); p.block_n = w.block_n;
-      p.frame_mask = h->mask; p.rate = io.rate; p.out_rows = static_cast<int>(io.rows);
-      p.up_s = sc; p.up_p = sc / 2 + sc % 2; p.up_cout = co;
-      ConvGemmEpilogue e{};
-      e.bias = w.bias; e.scale = 1.f; e.post_scale = 1.f;
-      e.out_hi = h->x0; e.out_bf_ld = co; e.out_act = h->xa0; e.out_act_slope = slope; e.out_act_ld = co;
-      p.ep = e;
-      JB_PROPAGATE(conv_gemm_tc(p, s));
+      const int pp = sc / 2 + sc % 2;
+      for (int q = 0; q < sc; ++q) {
+        ConvGemmProblem p{};
+        p.a_hi = h->y[cur]; p.a_rows = static_cast<int>(in_io.rows); p.a_ld = c_in; p.a_cols = c_in;
+        p.w_hi = w.hi; p.taps = 2; p.n_pad = w.n_pad; p.k_pad = w.k_pad;
+        // tap 0 reads x[j-1], tap 1 reads x[j]; GEMM row r is j (q >= p) or j-1 (q < p, whose j = 0 row
+        // would land on a negative output row), so that view row == GEMM row and no coordinate is negative
+        p.tap_off0 = q >= pp ? -1 : 0; p.tap_stride = 1;
+        p.w_row0 = w.n_pad + q * co; p.w_tap_stride = -w.n_pad; p.w_rows_total = 2 * w.n_pad;  // packed [x[j] taps | x[j-1] taps]
+        p.n = co; p.m_rows = static_cast<int>(in_io.rows); p.block_n = co > 256 ? 256 : co;
+        p.frame_mask = h->mask; p.rate = io.rate; p.out_rows = static_cast<int>(io.rows);
+        // output view = every s-th row starting at the first non-negative output row of this phase
+        const long long first = q >= pp ? q - pp : q - pp + sc;
+        p.mask_mul = sc; p.mask_add = static_cast<int>(first);
+        p.store_row_off = 0; p.out_pitch_mul = sc;
+        p.out_view_rows = static_cast<int>((io.rows - first + sc - 1) / sc);
+        ConvGemmEpilogue e{};
+        e.bias = w.bias; e.scale = 1.f; e.post_scale = 1.f;
+        e.out_hi = h->x0 + first * co; e.out_bf_ld = co;
+        e.out_act = h->xa0 + first * co; e.out_act_slope = slope; e.out_act_ld = co;
+        p.ep = e;
+        JB_REQUIRE(conv_gemm_tc2_eligible(p), JATTS_E_UNSUPPORTED, "transposed-conv phase not eligible for the TMA kernel");
+        JB_PROPAGATE(conv_gemm_tc2(p, s));
+      }
     }
     const bool last_stage = i == c.n_upsamples - 1;
     const float next_slope = last_stage ? 0.01f : slope;  // torch.nn.LeakyReLU() default before output_conv
