@@ -71,6 +71,9 @@ struct ConvGemmProblem {
 int conv_gemm_tc(const ConvGemmProblem& p, cudaStream_t stream);
 bool conv_gemm_tc2_eligible(const ConvGemmProblem& p);
 int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream);
+// fp16-split GEMMs (FastSpeech2) with the TMA-staged epilogue (conv_gemm_tc3.cu)
+bool conv_gemm_tc3_eligible(const ConvGemmProblem& p);
+int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream);
 // Plain CUDA-core kernel with identical semantics; used ONLY by the test entry point to bisect
 // tensor-core kernel bugs from host-side packing bugs.  Never on the product path.
 int conv_gemm_simt_debug(const ConvGemmProblem& p, cudaStream_t stream);

@@ -551,6 +551,8 @@ int conv_gemm_tc(const ConvGemmProblem& p, cudaStream_t stream) {
   JB_PROPAGATE(validate(p));
   static const bool no_tc2 = getenv("JATTS_B200_NO_TC2") != nullptr;  // A/B switch for profiling
   if (!no_tc2 && conv_gemm_tc2_eligible(p)) return conv_gemm_tc2(p, stream);
+  static const bool no_tc3 = getenv("JATTS_B200_NO_TC3") != nullptr;
+  if (!no_tc3 && conv_gemm_tc3_eligible(p)) return conv_gemm_tc3(p, stream);
   const bool split = p.a_lo != nullptr;
   switch (p.block_n) {
     case 32: return split ? launch<32, true>(p, stream) : launch<32, false>(p, stream);
