@@ -263,6 +263,9 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       constexpr uint32_t idesc = make_idesc(BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
       const int pipe = warp == 1 ? 0 : 1;
       const uint32_t w_addr = smem_u32(w_base);
+      // descriptor words: lo = (addr >> 4) | LBO(1) << 16 ; hi = SBO (8 rows) | version 1 | swizzle mode
+      constexpr uint32_t desc_lo0 = 1u << 16;
+      constexpr uint32_t desc_hi = static_cast<uint32_t>((8 * KCH * 2) >> 4) | (1u << 14) | (static_cast<uint32_t>(KCH == 64 ? 2 : 4) << 29);
       bool weights_ready = MODE != MODE_RESIDENT;
       for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
         if (P.mma_pipes == 2 ? (seq & 1) != pipe : pipe != 0) continue;
@@ -316,14 +319,11 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
               // tap t reads activation rows [t*dilation, t*dilation + 128) of the slab: a row-shifted
               // start address.  Measured on B200: the swizzle is a function of the absolute smem address
               // bits, so a start that is not 1024 B aligned needs NO base_offset in the descriptor.
-              const uint32_t a_addr = slab + static_cast<uint32_t>(tap * P.tap_stride) * C::KROWB;
-              const uint64_t da = make_kmajor_desc<KCH>(a_addr);
-              const uint64_t db = make_kmajor_desc<KCH>(b_addr);
+              const uint32_t a_lo = desc_lo0 + ((slab + static_cast<uint32_t>(tap * P.tap_stride) * C::KROWB) >> 4);
+              const uint32_t b_lo = desc_lo0 + (b_addr >> 4);
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                const uint64_t koff = static_cast<uint64_t>((k * UMMA_K2 * 2) >> 4);
-                tc_mma_bf16(tmem_d, da + koff, db + koff, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < KSTEPS; ++k)
+                tc_mma_bf16_lohi(tmem_d, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (kc | tap | k) != 0 ? 1u : 0u);
               if (MODE == MODE_HALO) tc_commit(&empty_bar[bs]);
             }
             tc_commit(&aempty_bar[as]);

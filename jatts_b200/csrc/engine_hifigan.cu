@@ -83,7 +83,9 @@ static int run_conv(const ConvW& w, const bf16* a, int a_cols, const StageIO& io
   if (ep.scale == 0.f) ep.scale = 1.f;
   if (ep.post_scale == 0.f) ep.post_scale = 1.f;
   p.ep = ep;
-  return conv_gemm_tc(p, s);
+  // the engine relies on the TMA epilogue storing every row (gap rows as zeros): no silent fallback
+  JB_REQUIRE(conv_gemm_tc2_eligible(p), JATTS_E_UNSUPPORTED, "convolution not eligible for the TMA-epilogue kernel");
+  return conv_gemm_tc2(p, s);
 }
 
 }  // namespace jb
@@ -191,12 +193,13 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
   const int in_pad = round_up(c.in_channels, 64);
   const float slope = c.lrelu_slope;
   // mel re-normalisation (vocoder.py:57-61) fused into the operand conversion
-  JB_PROPAGATE(zero_gap_rows(h->mel, in_pad * 2, L, 1, s));
+  // Gap rows: every tensor-core launch below stores EVERY row of its output (rows outside an utterance
+  // as zeros, through the TMA epilogue) and pack_mel_affine zero-fills the gap rows of the mel operand,
+  // so no buffer needs a separate zeroing pass.
   JB_PROPAGATE(pack_mel_affine(d_mel, c.in_channels, h->mel_scale, h->mel_shift, L, d_off, h->mel, in_pad, s));
   StageIO io{h->mask, 1, hl.n_rows};
   int cur = 0;  // y[cur] holds leaky_relu(stage input)
   {
-    JB_PROPAGATE(zero_gap_rows(h->y[cur], c.channels * 2, L, 1, s));
     ConvGemmEpilogue e{};
     e.out_act = h->y[cur]; e.out_act_slope = slope; e.out_act_ld = c.channels;
     JB_PROPAGATE(run_conv(h->input_conv, h->mel, in_pad, io, 1, e, s));
@@ -209,9 +212,6 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
     io.rate = h->rate[i];
     io.rows = static_cast<long long>(hl.n_rows) * io.rate;
     const int nxt = cur ^ 1;
-    // operand buffers of this stage: gap rows must be zero at this rate
-    bf16* operands[] = {h->xa0, h->xa, h->t, h->y[nxt]};
-    for (bf16* b : operands) JB_PROPAGATE(zero_gap_rows(b, co * 2, L, io.rate, s));
     {
       // ConvTranspose1d(k = 2s, stride s, padding p): out[j*s + q - p] = x[j] W[:,:,q] + x[j-1] W[:,:,q+s]
       // (SURVEY appendix C).  Each output phase q is a plain 2-tap convolution over the INPUT rows whose

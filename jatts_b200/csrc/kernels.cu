@@ -618,10 +618,14 @@ __global__ void pack_mel_affine_kernel(const float* __restrict__ mel, int c, con
                                        bf16* __restrict__ out, int out_ld) {
   const int r = blockIdx.x;
   const int b = L.frame_seg[r];
-  if (b < 0) return;
+  if (b < 0) {  // gap row: the operand buffer must read as zero padding here
+    for (int i = threadIdx.x; i < out_ld; i += blockDim.x) out[static_cast<long long>(r) * out_ld + i] = __float2bfloat16_rn(0.f);
+    return;
+  }
   const long long irow = off[b] + (r - L.seg_start[b]);
-  for (int i = threadIdx.x; i < c; i += blockDim.x)
-    out[static_cast<long long>(r) * out_ld + i] = __float2bfloat16_rn(mel[irow * c + i] * a[i] + bb[i]);
+  for (int i = threadIdx.x; i < out_ld; i += blockDim.x)
+    out[static_cast<long long>(r) * out_ld + i] =
+        i < c ? __float2bfloat16_rn(mel[irow * c + i] * a[i] + bb[i]) : __float2bfloat16_rn(0.f);
 }
 int pack_mel_affine(const float* mel, int c, const float* a, const float* b, RowLayout L, const int* off, bf16* out,
                     int out_ld, cudaStream_t s) {
