@@ -378,11 +378,241 @@ static int launch_attention(const float* qkv, const float* pos, const float* bia
   JB_KERNEL_OK();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Register-tiled variant for utterances up to ~440 positions (every shipped workload): one CTA =
+// 64 query rows x (utterance, head), 256 threads, 4 rows x 4 keys per thread in the two score passes
+// (8 FMA per shared-memory load instead of 3.2), float4-along-keys in the P.V pass.  The bias terms are
+// split off the dot products: (q+u).k = q.k + u.k and (q+v).p = q.p + v.p, so one copy of the 65 query
+// rows serves both passes; u.k / v.p are one extra 192-long dot per key / position of each tile.
+// ------------------------------------------------------------------------------------------------
+static constexpr int ATT64_R = 64;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+relpos_attention64_kernel(const float* __restrict__ qkv, const float* __restrict__ pos,
+                          const float* __restrict__ bias_u, const float* __restrict__ bias_v, int d_model, int dk,
+                          RowLayout L, int t_pad, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int out_ld) {
+  constexpr int R = ATT64_R;
+  const int b = blockIdx.y, h = blockIdx.z;
+  const int T = L.seg_len[b];
+  const int a0 = blockIdx.x * R;
+  if (a0 >= T) return;
+  const long long base = L.seg_start[b];
+  const int ks = dk + 4;
+  extern __shared__ float sm[];
+  float* q = sm;                         // [R+1][ks]   raw queries (row R = first row of the next tile)
+  float* S = q + (R + 1) * ks;           // [R][t_pad]
+  float* tile = S + R * t_pad;           // [ATT_TK][ks]
+  float* cvec = tile + ATT_TK * ks;      // [ATT_TK]    u.k (pass A) / v.p (pass B) of the tile
+  float* ub = cvec + ATT_TK;             // [dk] bias_u of this head, then [dk] bias_v
+  const int tid = threadIdx.x;
+  const int ld3 = 3 * d_model;
+  const int dk4 = dk >> 2;
+  const int tx = tid & 15, ty = tid >> 4;   // 16 key lanes (4 keys each: tx, tx+16, tx+32, tx+48), 16 row groups of 4
+
+  for (int i = tid; i < (R + 1) * dk4; i += ATT_THREADS) {
+    const int r = i / dk4, d4 = i - r * dk4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a0 + r < T) v = *reinterpret_cast<const float4*>(qkv + (base + a0 + r) * ld3 + h * dk + d4 * 4);
+    *reinterpret_cast<float4*>(q + r * ks + d4 * 4) = v;
+  }
+  for (int i = tid; i < 2 * dk; i += ATT_THREADS) ub[i] = i < dk ? bias_u[h * dk + i] : bias_v[h * dk + i - dk];
+  __syncthreads();
+
+  // load one 64-row tile of k / p / v (zero rows past T) and, for the score passes, bias . row
+  auto load_tile = [&](const float* src, long long row_stride, int r0, const float* bias_vec) {
+    for (int i = tid; i < ATT_TK * dk4; i += ATT_THREADS) {
+      const int kk = i / dk4, d4 = i - kk * dk4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + kk < T) v = *reinterpret_cast<const float4*>(src + static_cast<long long>(r0 + kk) * row_stride + d4 * 4);
+      *reinterpret_cast<float4*>(tile + kk * ks + d4 * 4) = v;
+    }
+    __syncthreads();
+    if (bias_vec) {
+      const int kk = tid >> 2, part = tid & 3;   // 4 threads per row, dk/4 elements each
+      float acc = 0.f;
+      const int per = dk >> 2;
+      for (int d = part * per; d < (part + 1) * per; ++d) acc += tile[kk * ks + d] * bias_vec[d];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) cvec[kk] = acc;
+      __syncthreads();
+    }
+  };
+
+  // ---- pass A: S[r][key] = q_a . k_key + u . k_key
+  for (int k0 = 0; k0 < T; k0 += ATT_TK) {
+    load_tile(qkv + base * ld3 + d_model + h * dk, ld3, k0, ub);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int d = 0; d < dk; d += 4) {
+      float4 qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(q + (ty * 4 + i) * ks + d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4*>(tile + (tx + 16 * j) * ks + d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] += (qv[i].x * kv[j].x + qv[i].y * kv[j].y) + (qv[i].z * kv[j].z + qv[i].w * kv[j].w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int key = k0 + tx + 16 * j;
+      if (key < T) {
+        const float cu = cvec[tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) S[(ty * 4 + i) * t_pad + key] = acc[i][j] + cu;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- pass B: BD[a][n] = q_a . p_n + v . p_n, scattered through the closed-form legacy rel-shift
+  for (int n0 = 0; n0 < T; n0 += ATT_TK) {
+    load_tile(pos + h * dk, d_model, n0, ub + dk);
+    float acc[5][4];   // rows ty*4 .. ty*4+4 (the extra row feeds the "a+1" branch of the shift)
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int d = 0; d < dk; d += 4) {
+      float4 qv[5], pv[4];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) qv[i] = *reinterpret_cast<const float4*>(q + (ty * 4 + i) * ks + d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pv[j] = *reinterpret_cast<const float4*>(tile + (tx + 16 * j) * ks + d);
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] += (qv[i].x * pv[j].x + qv[i].y * pv[j].y) + (qv[i].z * pv[j].z + qv[i].w * pv[j].w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n < T) {
+        const float cv = cvec[tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = ty * 4 + i;
+          const int a = a0 + r;
+          if (a < T) {
+            const int b1 = n - (T - 1 - a);
+            if (b1 >= 0 && b1 <= a) S[r * t_pad + b1] += acc[i][j] + cv;
+            const int b2 = n + a + 2;
+            if (b2 < T) S[r * t_pad + b2] += acc[i + 1][j] + cv;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- softmax over keys (scores / sqrt(dk))
+  {
+    const float scale = rsqrtf(static_cast<float>(dk));
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < R; r += ATT_THREADS / 32) {
+      if (a0 + r >= T) continue;
+      float* row = S + r * t_pad;
+      float m = -INFINITY;
+      for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
+      m = warp_max(m) * scale;
+      float sum = 0.f;
+      for (int j = lane; j < T; j += 32) {
+        const float e = expf(row[j] * scale - m);
+        row[j] = e;
+        sum += e;
+      }
+      const float inv = 1.0f / warp_sum(sum);
+      for (int j = lane; j < T; j += 32) row[j] *= inv;
+      for (int j = T + lane; j < t_pad; j += 32) row[j] = 0.f;   // the P.V pass reads keys in groups of 4
+    }
+  }
+  __syncthreads();
+
+  // ---- ctx = P . V : thread = (16-row group, dim lane), 3 dims (d, d+64, d+128), keys 4 at a time
+  const int dx = tid & 63, rg = tid >> 6;
+  float ctx[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
+  for (int k0 = 0; k0 < T; k0 += ATT_TK) {
+    load_tile(qkv + base * ld3 + 2 * d_model + h * dk, ld3, k0, nullptr);
+    const int kn = min(ATT_TK, T - k0);
+    for (int kk = 0; kk < kn; kk += 4) {
+      float vv[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int d = dx + 64 * j;
+          vv[u][j] = d < dk ? tile[(kk + u) * ks + d] : 0.f;   // rows past T are zero-filled
+        }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 p = *reinterpret_cast<const float4*>(S + (rg * 16 + i) * t_pad + k0 + kk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          ctx[i][j] += (p.x * vv[0][j] + p.y * vv[1][j]) + (p.z * vv[2][j] + p.w * vv[3][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int a = a0 + rg * 16 + i;
+    if (a >= T) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = dx + 64 * j;
+      if (d < dk) {
+        bf16 hh, ll;
+        split_op16(ctx[i][j], hh, ll);
+        out_hi[(base + a) * out_ld + h * dk + d] = hh;
+        if (out_lo) out_lo[(base + a) * out_ld + h * dk + d] = ll;
+      }
+    }
+  }
+}
+
+static int launch_attention64(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
+                              int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld,
+                              cudaStream_t s, bool* launched) {
+  const int dk = d_model / n_head;
+  const int t_pad = round_up(max_len, 4) + 4;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(ATT64_R + 1) * (dk + 4) + static_cast<size_t>(ATT64_R) * t_pad +
+                                       ATT_TK * (dk + 4) + ATT_TK + 2 * dk);
+  *launched = false;
+  if (smem > 227 * 1024 || (dk & 15) != 0) return 0;   // too long for this variant: caller falls back
+  static size_t attr = 0;
+  if (smem > attr) {
+    JB_CUDA_OK(cudaFuncSetAttribute(relpos_attention64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  dim3 grid(ceil_div(max_len, ATT64_R), L.nseg, n_head);
+  relpos_attention64_kernel<<<grid, ATT_THREADS, smem, s>>>(qkv, pos, bias_u, bias_v, d_model, dk, L, t_pad, out_hi, out_lo, out_ld);
+  JB_KERNEL_OK();
+  *launched = true;
+  return 0;
+}
+
 int relpos_attention(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
                      int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s) {
   const int dk = d_model / n_head;
   JB_REQUIRE(dk * n_head == d_model && dk % 4 == 0 && dk <= 256, -2, "attention: d_k must be a multiple of 4, <= 256");
   if (L.nseg == 0 || max_len == 0) return 0;
+  {
+    bool launched = false;
+    JB_PROPAGATE(launch_attention64(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched));
+    if (launched) return 0;
+  }
   if (max_len <= 1800) return launch_attention<16>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
   if (max_len <= 4000) return launch_attention<8>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
   return launch_attention<4>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
