@@ -28,7 +28,7 @@ namespace jb {
 
 static constexpr int BLOCK_M2 = 128;
 static constexpr int UMMA_K2 = 16;
-static constexpr int kThreads2 = 416;  // producer, MMA x2 (warps 1, 12), loader, store, 8 epilogue warps
+static constexpr int kThreads2 = 384;  // producer, MMA issuer, loader, store, 2 x 4 epilogue warps
 enum : int { MODE_STREAM = 0, MODE_HALO = 1, MODE_RESIDENT = 2 };
 
 struct KernelParams2 {
@@ -52,7 +52,6 @@ struct KernelParams2 {
   int w_row0, w_tap_stride;       // weight rows of tap t: w_row0 + t*w_tap_stride (+ n0)
   int store_row_off;              // output row coordinate = m0 + store_row_off
   int mask_mul, mask_add, out_rows;  // validity: frame_mask[(row*mask_mul + mask_add) / rate], 0 <= . < out_rows
-  int mma_pipes;    // 1: warp 1 issues every tile; 2: warps 1 and 12 issue alternate tiles (small N: issue bound)
   long long* trace; // debug: per-role clock64 timeline of CTA 0 (jatts_debug_set_trace), else null
 };
 
@@ -102,21 +101,18 @@ struct Cfg2 {
   static_assert(A_STAGES <= 4 && STAGES <= 8 && B_STAGES <= 8, "barrier arrays");
 };
 
-// Ring position of item `inner` (0..per_tile-1) of the tile with sequence number `seq`.  Tiles alternate
-// between two independent pipelines (even / odd seq); each pipeline owns half of every ring so that every
-// mbarrier has exactly one producer and one consumer walking it in lockstep (an mbarrier parity wait
-// cannot tell "two phases ahead" from "done", so a consumer must never share a barrier with a faster one).
-struct RingPos { int idx; uint32_t phase; };
-__device__ __forceinline__ RingPos ring_pos(int seq, int inner, int per_tile, int depth, int npipe = 2) {
-  // npipe == 1: one consumer walks the whole ring; npipe == 2: each pipeline owns depth/2 slots
-  const int pipe = npipe == 2 ? (seq & 1) : 0;
-  const int depth_per_pipe = npipe == 2 ? depth >> 1 : depth;
-  const uint32_t cnt = static_cast<uint32_t>(npipe == 2 ? seq >> 1 : seq) * per_tile + inner;
-  RingPos r;
-  r.idx = pipe * depth_per_pipe + static_cast<int>(cnt % depth_per_pipe);
-  r.phase = (cnt / depth_per_pipe) & 1u;
-  return r;
-}
+// Ring cursor: slot index + mbarrier phase parity, advanced incrementally (no integer divisions on the
+// per-tile critical path).  Every mbarrier has exactly one producer and one consumer walking it in
+// lockstep -- an mbarrier parity wait cannot tell "two phases ahead" from "done", so the two epilogue
+// groups (even / odd tiles) own disjoint halves of the epilogue ring: slots [base, base + depth).
+struct Ring {
+  int idx, base, depth;
+  uint32_t phase;
+  __device__ __forceinline__ Ring(int base_, int depth_) : idx(base_), base(base_), depth(depth_), phase(0) {}
+  __device__ __forceinline__ void next() {
+    if (++idx == base + depth) { idx = base; phase ^= 1u; }
+  }
+};
 
 // K-major operand tile with rows of exactly one swizzle span (128 B: KCH = 64, 64 B: KCH = 32)
 template <int KCH>
@@ -216,59 +212,58 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             tma_load_2d(&tm_b, wfull_bar, w_base + (kc * P.taps + tap) * C::B_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride);
       }
       const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * C::KROWB;
+      Ring rs(0, STAGES), ra(0, C::A_STAGES), rb(0, C::B_STAGES);
       for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
         const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
         const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
         if (MODE == MODE_STREAM) {
-          const int k_iters = P.taps * P.k_chunks;
-          int it = 0;
           for (int tap = 0; tap < P.taps; ++tap) {
             const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
             const int brow = P.w_row0 + tap * P.w_tap_stride + n0;
-            for (int kc = 0; kc < P.k_chunks; ++kc, ++it) {
-              const RingPos rp = ring_pos(seq, it, k_iters, STAGES, P.mma_pipes);
-              mbar_wait(&empty_bar[rp.idx], rp.phase ^ 1);
-              uint8_t* st = smem + rp.idx * C::STAGE_BYTES;
-              mbar_expect_tx(&full_bar[rp.idx], C::STAGE_BYTES);
-              tma_load_2d(&tm_a, &full_bar[rp.idx], st, kc * KCH, arow);
-              tma_load_2d(&tm_b, &full_bar[rp.idx], st + C::A_BYTES, kc * KCH, brow);
+            for (int kc = 0; kc < P.k_chunks; ++kc) {
+              mbar_wait(&empty_bar[rs.idx], rs.phase ^ 1);
+              uint8_t* st = smem + rs.idx * C::STAGE_BYTES;
+              mbar_expect_tx(&full_bar[rs.idx], C::STAGE_BYTES);
+              tma_load_2d(&tm_a, &full_bar[rs.idx], st, kc * KCH, arow);
+              tma_load_2d(&tm_b, &full_bar[rs.idx], st + C::A_BYTES, kc * KCH, brow);
+              rs.next();
             }
           }
         } else {
           for (int kc = 0; kc < P.k_chunks; ++kc) {
-            const RingPos ra = ring_pos(seq, kc, P.k_chunks, C::A_STAGES, P.mma_pipes);
             mbar_wait(&aempty_bar[ra.idx], ra.phase ^ 1);
             if (kc == 0) JB_TRACE(0, 0, seq);
             mbar_expect_tx(&afull_bar[ra.idx], a_bytes);
             tma_load_2d(&tm_a, &afull_bar[ra.idx], smem + ra.idx * C::A_SLAB_BYTES, kc * KCH, m0 + P.tap_off0);
+            ra.next();
             if (MODE == MODE_HALO) {
               for (int tap = 0; tap < P.taps; ++tap) {
-                const RingPos rb = ring_pos(seq, kc * P.taps + tap, P.k_chunks * P.taps, C::B_STAGES, P.mma_pipes);
                 mbar_wait(&empty_bar[rb.idx], rb.phase ^ 1);
                 mbar_expect_tx(&full_bar[rb.idx], C::B_BYTES);
                 tma_load_2d(&tm_b, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride + n0);
+                rb.next();
               }
             }
           }
         }
       }
     }
-  } else if (warp == 1 || warp == 12) {
-    // ===================== MMA issuers (two pipelines: even / odd tiles) =====================
-    // Measured (tools_gpu_trace.py): for N <= 64 a single issuing thread is the bottleneck -- ~57 clk to
-    // issue one tcgen05.mma that executes in 16-32 clk, plus ~450 clk per mbarrier wait.  Two warps issue
-    // alternate tiles into their own TMEM accumulator; ring positions are computed from the tile sequence
-    // number so both consumers walk the same rings without talking to each other.
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // Measured (tools_gpu_trace.py): for N <= 64 this single issuing thread is the bottleneck -- ~46 clk to
+    // issue one tcgen05.mma that executes in 16-32 clk, plus several hundred clk of mbarrier handling per
+    // tile.  A second issuing warp made it worse (84 clk per MMA: the issue port is shared).  Tiles alternate
+    // between the two TMEM accumulators / epilogue groups.
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
-      const int pipe = warp == 1 ? 0 : 1;
+      const int pipe = 0;
+      Ring rs(0, STAGES), ra(0, C::A_STAGES), rb(0, C::B_STAGES);
       const uint32_t w_addr = smem_u32(w_base);
       // descriptor words: lo = (addr >> 4) | LBO(1) << 16 ; hi = SBO (8 rows) | version 1 | swizzle mode
       constexpr uint32_t desc_lo0 = 1u << 16;
       constexpr uint32_t desc_hi = static_cast<uint32_t>((8 * KCH * 2) >> 4) | (1u << 14) | (static_cast<uint32_t>(KCH == 64 ? 2 : 4) << 29);
       bool weights_ready = MODE != MODE_RESIDENT;
       for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
-        if (P.mma_pipes == 2 ? (seq & 1) != pipe : pipe != 0) continue;
         const int acc = seq & 1;   // accumulator (and epilogue group) of this tile
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
         mbar_wait(&tempty_bar[acc], ((seq >> 1) & 1) ^ 1);
@@ -282,9 +277,9 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         if (MODE == MODE_STREAM) {
           const int k_iters = P.taps * P.k_chunks;
           for (int it = 0; it < k_iters; ++it) {
-            const RingPos rp = ring_pos(seq, it, k_iters, STAGES, P.mma_pipes);
-            const int stage = rp.idx;
-            mbar_wait(&full_bar[stage], rp.phase);
+            const int stage = rs.idx;
+            mbar_wait(&full_bar[stage], rs.phase);
+            rs.next();
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint64_t da = make_kmajor_desc<KCH>(sa);
@@ -298,9 +293,9 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           }
         } else {
           for (int kc = 0; kc < P.k_chunks; ++kc) {
-            const RingPos ra = ring_pos(seq, kc, P.k_chunks, C::A_STAGES, P.mma_pipes);
             const int as = ra.idx;
             mbar_wait(&afull_bar[as], ra.phase);
+            ra.next();
             if (pipe == 0 && kc == 0) JB_TRACE(1, 1, seq);
             tc_fence_after();
             const uint32_t slab = smem_u32(smem + as * C::A_SLAB_BYTES);
@@ -308,9 +303,9 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
               uint32_t b_addr;
               int bs = 0;
               if (MODE == MODE_HALO) {
-                const RingPos rb = ring_pos(seq, kc * P.taps + tap, P.k_chunks * P.taps, C::B_STAGES, P.mma_pipes);
                 bs = rb.idx;
                 mbar_wait(&full_bar[bs], rb.phase);
+                rb.next();
                 tc_fence_after();
                 b_addr = smem_u32(b_base + bs * C::B_BYTES);
               } else {
@@ -337,13 +332,15 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     // ===================== epilogue loader =====================
     if (elect_one()) {
       const uint32_t bytes = (P.has_res ? C::SLAB_BYTES : 0) + (P.has_acc ? C::SLAB_BYTES : 0);
+      Ring rg0(0, E / 2), rg1(E / 2, E / 2);   // the two epilogue groups' halves of the ring
       for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+        Ring& re = (seq & 1) ? rg1 : rg0;
         const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
         const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
         for (int s = 0; s < C::N_SLABS; ++s) {
-          const RingPos re = ring_pos(seq, s, C::N_SLABS, E);
           const int e = re.idx;
           mbar_wait(&epempty_bar[e], re.phase ^ 1);
+          re.next();
           if (s == 0) JB_TRACE(2, 0, seq);
           uint8_t* buf = ep_base + e * entry_bytes;
           if (bytes) {
@@ -362,13 +359,15 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       int groups = 0;
       int hist0 = 0, hist1 = 0;   // entries of the two most recently committed store groups
       const int depth = P.store_depth;   // older groups kept in flight behind the one just committed (0..2)
+      Ring rg0(0, E / 2), rg1(E / 2, E / 2);
       for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+        Ring& re = (seq & 1) ? rg1 : rg0;
         const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
         const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
         for (int s = 0; s < C::N_SLABS; ++s) {
-          const RingPos re = ring_pos(seq, s, C::N_SLABS, E);
           const int e = re.idx;
           mbar_wait(&ready_bar[e], re.phase);  // the 128 threads of the tile's epilogue group wrote + fenced this slab
+          re.next();
           if (s == 0) JB_TRACE(3, 0, seq);
           uint8_t* bufA = ep_base + e * entry_bytes;
           if (P.has_out0) tma_store_2d(&tm_out0, bufA, n0 + s * C::SLAB, m0 + P.store_row_off);
@@ -403,6 +402,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     const uint32_t sw = (row_off >> 7) & C::SW_MASK;   // XOR pattern of this row's 16-byte chunks
     const int acc = pipe;
     uint32_t n_done = 0;
+    Ring re(pipe * (E / 2), E / 2);
     // row validity of this group's NEXT tile is fetched while the current one is processed; the raw byte
     // stays in a register and is only compared one tile later, so the load is off the critical path
     auto row_valid = [&](int tile) -> unsigned {
@@ -438,9 +438,9 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             tmem_ld16(ta, r0);
           }
         }
-        const RingPos re = ring_pos(seq, s, C::N_SLABS, E);
         const int e = re.idx;
         mbar_wait(&epfull_bar[e], re.phase);   // residual / branch-sum slabs have landed (or entry is free)
+        re.next();
         if (s == 0 && warp == 4 && lane == 0) JB_TRACE(4, 1, seq);
         tmem_ld_wait();
         if (s == C::N_SLABS - 1) {
@@ -592,9 +592,6 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.ep_entries = entries;
   kp.w_bytes = w_bytes;
   kp.trace = g_trace_ptr;
-  static const char* mp_env = getenv("JATTS_B200_MMA_PIPES");
-  // measured: two issuing warps contend for the tensor-core issue port (84 vs 57 clk per MMA) -- one is better
-  kp.mma_pipes = (mp_env && atoi(mp_env) == 2) ? 2 : 1;
   kp.store_depth = entries >= 6 ? 2 : (entries >= 4 ? 1 : 0);
   static const char* sd_env = getenv("JATTS_B200_STORE_DEPTH");
   if (sd_env) kp.store_depth = atoi(sd_env) < entries - 1 ? atoi(sd_env) : entries - 2;
