@@ -305,7 +305,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<*, bf16> (all HiFi-GAN Conv1d/ConvTranspose1d launches of one step)",
+        "roofline": {"bound": "tensor", "kernel": "conv_bf16_tma_kernel<*> (all HiFi-GAN Conv1d/ConvTranspose1d launches of one step)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": None,
                      "launches_per_step": int(prof["n_bf16"]), "kernel_ms_per_step": prof["ms_bf16"],
