@@ -603,11 +603,275 @@ static int launch_attention64(const float* qkv, const float* pos, const float* b
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variant (legacy warp-level MMA, m16n8k8 TF32) with the 3xTF32 split: x = hi + lo with
+// hi = x truncated to TF32 (exact remainder lo = x - hi, rounded to TF32); a.b ~= hi.hi + hi.lo + lo.hi
+// accumulated in fp32, which keeps scores and context FP32-faithful (the dropped lo.lo term is ~2^-21
+// relative).  tcgen05 is not used here: the operands are per-(utterance, head) 64 x d_k tiles that need a
+// register-level split and a scatter epilogue (the rel-shift), which the warp-level fragment layout gives
+// directly.
+//
+// One CTA = 64 query rows a0..a0+63 of one (utterance, head), of which it OWNS the first 63: the legacy
+// rel-shift sends BD[a'][n] = (q_a' + v) . p_n to row a' (keys <= a') and to row a'-1 (keys >= a'+1), so
+// row r is complete once BD rows r and r+1 are known; tiles advance by 63 rows and the 64th row only
+// contributes its BD.  8 warps = 4 row blocks of 16 x 2 halves of the 64-key tile (score passes) or of the
+// head dimension (P.V pass).  The biases are added while the A fragments are built ((q+u).k, (q+v).p as
+// the reference computes them).  The next k / p / v tile is prefetched into registers while the current
+// one is in the MMAs.  Shared-memory strides: d_k+4 (== 4 mod 32) for operands read as [g][t], d_k+8
+// (== 8 mod 32) for the V tile read as [t][g], t_pad with t_pad/4 odd: fragment loads are conflict-free.
+// ------------------------------------------------------------------------------------------------
+static constexpr int ATT_MMA_OWN = 63;
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;   // the MMA ignores the low 13 bits: +half ulp = round
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], float b0,
+                                           float b1) {
+  uint32_t b0h, b0l, b1h, b1l;
+  split_tf32(b0, b0h, b0l);
+  split_tf32(b1, b1h, b1l);
+  mma_tf32(c, alo, b0h, b1h);
+  mma_tf32(c, ahi, b0l, b1l);
+  mma_tf32(c, ahi, b0h, b1h);
+}
+
+template <int DK>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+relpos_attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ pos,
+                            const float* __restrict__ bias_u, const float* __restrict__ bias_v, int d_model,
+                            RowLayout L, int t_pad, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int out_ld) {
+  constexpr int R = 64;
+  constexpr int KS = DK + 4;    // q / k / p row stride (words)
+  constexpr int KV = DK + 8;    // v row stride
+  constexpr int DK4 = DK / 4;
+  constexpr int NT_C = DK / 16; // 8-wide n-tiles per warp in the P.V pass
+  constexpr int NPRE = ATT_TK * DK4 / ATT_THREADS;   // float4 per thread per tile
+  static_assert(ATT_TK * DK4 % ATT_THREADS == 0, "tile must divide evenly over the CTA");
+  const int b = blockIdx.y, h = blockIdx.z;
+  const int T = L.seg_len[b];
+  const int a0 = blockIdx.x * ATT_MMA_OWN;
+  if (a0 >= T) return;
+  const long long base = L.seg_start[b];
+  extern __shared__ float sm[];
+  float* q = sm;                         // [R][KS]
+  float* S = q + R * KS;                 // [R][t_pad]
+  float* tile = S + R * t_pad;           // [ATT_TK][KV]
+  float* ub = tile + ATT_TK * KV;        // [2*DK] bias_u, bias_v of this head
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int rb = warp & 3, half = warp >> 2;
+  const int ld3 = 3 * d_model;
+  const int n_tiles = (T + ATT_TK - 1) / ATT_TK;
+
+  // tile jobs: n_tiles of k, n_tiles of p, n_tiles of v; job j+1 is fetched while job j is computed
+  float4 pre[NPRE];
+  auto fetch = [&](int job) {
+    const int pass = job / n_tiles, r0 = (job - pass * n_tiles) * ATT_TK;
+    const float* src = pass == 1 ? pos + h * DK : qkv + base * ld3 + (pass == 0 ? d_model : 2 * d_model) + h * DK;
+    const long long row_stride = pass == 1 ? d_model : ld3;
+#pragma unroll
+    for (int i = 0; i < NPRE; ++i) {
+      const int idx = tid + i * ATT_THREADS;
+      const int kk = idx / DK4, d4 = idx - kk * DK4;
+      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + kk < T) pre[i] = *reinterpret_cast<const float4*>(src + static_cast<long long>(r0 + kk) * row_stride + d4 * 4);
+    }
+  };
+  auto commit = [&](int stride) {
+#pragma unroll
+    for (int i = 0; i < NPRE; ++i) {
+      const int idx = tid + i * ATT_THREADS;
+      const int kk = idx / DK4, d4 = idx - kk * DK4;
+      *reinterpret_cast<float4*>(tile + kk * stride + d4 * 4) = pre[i];
+    }
+  };
+
+  fetch(0);
+  for (int i = tid; i < R * DK4; i += ATT_THREADS) {
+    const int r = i / DK4, d4 = i - r * DK4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a0 + r < T) v = *reinterpret_cast<const float4*>(qkv + (base + a0 + r) * ld3 + h * DK + d4 * 4);
+    *reinterpret_cast<float4*>(q + r * KS + d4 * 4) = v;
+  }
+  for (int i = tid; i < 2 * DK; i += ATT_THREADS) ub[i] = i < DK ? bias_u[h * DK + i] : bias_v[h * DK + i - DK];
+
+  // 16 rows (rb) x 32 tile rows (half) x DK:  acc[nt] = (q + bias) . tile^T
+  auto score_tile = [&](float (&acc)[4][4], const float* bias) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* qa = q + (rb * 16 + g) * KS + t;
+    const float* kb = tile + (half * 32 + g) * KS + t;
+    const float* bv = bias + t;
+#pragma unroll 4
+    for (int k = 0; k < DK; k += 8) {
+      uint32_t ahi[4], alo[4];
+      const float u0 = bv[k], u1 = bv[k + 4];
+      split_tf32(qa[k] + u0, ahi[0], alo[0]);
+      split_tf32(qa[8 * KS + k] + u0, ahi[1], alo[1]);
+      split_tf32(qa[k + 4] + u1, ahi[2], alo[2]);
+      split_tf32(qa[8 * KS + k + 4] + u1, ahi[3], alo[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_3xtf32(acc[nt], ahi, alo, kb[nt * 8 * KS + k], kb[nt * 8 * KS + k + 4]);
+    }
+  };
+
+  int job = 0;
+  // ---- pass A: S[r][key] = (q_a + u) . k_key
+  for (int k0 = 0; k0 < T; k0 += ATT_TK, ++job) {
+    commit(KS);
+    __syncthreads();
+    fetch(job + 1);
+    float acc[4][4];
+    score_tile(acc, ub);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = rb * 16 + g + (e >> 1) * 8;
+        const int key = k0 + half * 32 + nt * 8 + 2 * t + (e & 1);
+        if (key < T) S[r * t_pad + key] = acc[nt][e];
+      }
+    __syncthreads();
+  }
+
+  // ---- pass B: BD[a'][n] = (q_a' + v) . p_n lands in row a' (keys <= a') and row a'-1 (keys >= a'+1)
+  for (int n0 = 0; n0 < T; n0 += ATT_TK, ++job) {
+    commit(KS);
+    __syncthreads();
+    fetch(job + 1);
+    float acc[4][4];
+    score_tile(acc, ub + DK);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = rb * 16 + g + (e >> 1) * 8;
+        const int n = n0 + half * 32 + nt * 8 + 2 * t + (e & 1);
+        const int a = a0 + r;
+        if (n < T && a < T) {
+          const int b1 = n - (T - 1 - a);
+          if (b1 >= 0 && b1 <= a) S[r * t_pad + b1] += acc[nt][e];
+          const int b2 = n + a + 1;
+          if (r > 0 && b2 < T) S[(r - 1) * t_pad + b2] += acc[nt][e];
+        }
+      }
+    __syncthreads();
+  }
+
+  // ---- softmax over keys (scores / sqrt(dk)); the first v tile is already in flight
+  {
+    const float scale = rsqrtf(static_cast<float>(DK));
+    for (int r = warp; r < R; r += ATT_THREADS / 32) {
+      float* row = S + r * t_pad;
+      if (r >= ATT_MMA_OWN || a0 + r >= T) {   // rows that are not stored still enter the MMA: keep them finite
+        for (int j = lane; j < t_pad; j += 32) row[j] = 0.f;
+        continue;
+      }
+      float m = -INFINITY;
+      for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
+      m = warp_max(m) * scale;
+      float sum = 0.f;
+      for (int j = lane; j < T; j += 32) {
+        const float e = expf(row[j] * scale - m);
+        row[j] = e;
+        sum += e;
+      }
+      const float inv = 1.0f / warp_sum(sum);
+      for (int j = lane; j < T; j += 32) row[j] *= inv;
+      for (int j = T + lane; j < t_pad; j += 32) row[j] = 0.f;
+    }
+  }
+
+  // ---- ctx = P . V : warp = 16 rows x DK/2 dims
+  float ctx[NT_C][4];
+#pragma unroll
+  for (int i = 0; i < NT_C; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
+  for (int k0 = 0; k0 < T; k0 += ATT_TK, ++job) {
+    commit(KV);
+    __syncthreads();
+    if (job + 1 < 3 * n_tiles) fetch(job + 1);
+    const int kn = min(ATT_TK, T - k0);
+    const float* pa = S + (rb * 16 + g) * t_pad + k0 + t;
+    const float* vb = tile + t * KV + half * (DK / 2) + g;
+    for (int kk = 0; kk < kn; kk += 8) {
+      uint32_t ahi[4], alo[4];
+      split_tf32(pa[kk], ahi[0], alo[0]);
+      split_tf32(pa[8 * t_pad + kk], ahi[1], alo[1]);
+      split_tf32(pa[kk + 4], ahi[2], alo[2]);
+      split_tf32(pa[8 * t_pad + kk + 4], ahi[3], alo[3]);
+#pragma unroll
+      for (int nt = 0; nt < NT_C; ++nt) mma_3xtf32(ctx[nt], ahi, alo, vb[kk * KV + nt * 8], vb[(kk + 4) * KV + nt * 8]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT_C; ++nt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int r = rb * 16 + g + hr * 8;
+      const int a = a0 + r;
+      if (r >= ATT_MMA_OWN || a >= T) continue;
+      const int d = half * (DK / 2) + nt * 8 + 2 * t;
+      bf16 h0, l0, h1, l1;
+      split_op16(ctx[nt][hr * 2], h0, l0);
+      split_op16(ctx[nt][hr * 2 + 1], h1, l1);
+      const long long o = (base + a) * out_ld + h * DK + d;
+      *reinterpret_cast<uint32_t*>(out_hi + o) =
+          static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      if (out_lo)
+        *reinterpret_cast<uint32_t*>(out_lo + o) =
+            static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    }
+}
+
+template <int DK>
+static int launch_attention_mma(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
+                                int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld,
+                                cudaStream_t s, bool* launched) {
+  const int t_pad = round_up(max_len, 8) + 4;   // t_pad / 4 odd
+  const size_t smem = sizeof(float) * (static_cast<size_t>(64) * (DK + 4) + static_cast<size_t>(64) * t_pad +
+                                       ATT_TK * (DK + 8) + 2 * DK);
+  *launched = false;
+  if (smem > 227 * 1024 || (out_ld & 1)) return 0;
+  static size_t attr = 0;
+  if (smem > attr) {
+    JB_CUDA_OK(cudaFuncSetAttribute(relpos_attention_mma_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  dim3 grid(ceil_div(max_len, ATT_MMA_OWN), L.nseg, n_head);
+  relpos_attention_mma_kernel<DK><<<grid, ATT_THREADS, smem, s>>>(qkv, pos, bias_u, bias_v, d_model, L, t_pad, out_hi, out_lo, out_ld);
+  JB_KERNEL_OK();
+  *launched = true;
+  return 0;
+}
+
 int relpos_attention(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
                      int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s) {
   const int dk = d_model / n_head;
   JB_REQUIRE(dk * n_head == d_model && dk % 4 == 0 && dk <= 256, -2, "attention: d_k must be a multiple of 4, <= 256");
   if (L.nseg == 0 || max_len == 0) return 0;
+  if (!getenv("JATTS_B200_NO_ATT_MMA")) {
+    bool launched = false;
+    switch (dk) {
+      case 32: JB_PROPAGATE(launch_attention_mma<32>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched)); break;
+      case 64: JB_PROPAGATE(launch_attention_mma<64>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched)); break;
+      case 128: JB_PROPAGATE(launch_attention_mma<128>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched)); break;
+      case 192: JB_PROPAGATE(launch_attention_mma<192>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched)); break;
+      default: break;
+    }
+    if (launched) return 0;
+  }
   {
     bool launched = false;
     JB_PROPAGATE(launch_attention64(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched));
@@ -866,44 +1130,69 @@ int pack_mel_affine(const float* mel, int c, const float* a, const float* b, Row
 }
 
 // ------------------------------------------------------------------------------------------------
-// HiFi-GAN output_conv (C -> 1, k taps) + tanh; one thread per output sample
+// HiFi-GAN output_conv (C -> 1, k taps) + tanh.  One thread = OC_PER consecutive output samples: an
+// 8-channel slice of the k + OC_PER - 1 input rows is held in registers and every weight (one shared-memory
+// load) feeds OC_PER FMAs.
 // ------------------------------------------------------------------------------------------------
+static constexpr int OC_PER = 4;
+static constexpr int OC_MAXK = 7;
+
 __global__ void output_conv_tanh_kernel(const bf16* __restrict__ x, int ld, int c, const float* __restrict__ w,
                                         float bias, int k, RowLayout L, int rate, const int* __restrict__ frame_off,
                                         float* __restrict__ wave, long long total_rows) {
   extern __shared__ float ws[];  // [k][c]
   for (int i = threadIdx.x; i < k * c; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
-  const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (row >= total_rows) return;
-  const int fr = static_cast<int>(row / rate);
-  const int b = L.frame_seg[fr];
-  if (b < 0) return;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * OC_PER;
+  if (row0 >= total_rows) return;
   const int pad = (k - 1) / 2;
-  float acc = bias;
-  for (int j = 0; j < k; ++j) {
-    const long long rr = row + j - pad;  // gap rows are zero, so no per-tap boundary test is needed
-    if (rr < 0 || rr >= total_rows) continue;
-    const uint4* px = reinterpret_cast<const uint4*>(x + rr * ld);
-    for (int c8 = 0; c8 < c / 8; ++c8) {
-      const uint4 u = px[c8];
+  float acc[OC_PER];
+#pragma unroll
+  for (int o = 0; o < OC_PER; ++o) acc[o] = bias;
+  for (int c8 = 0; c8 < c / 8; ++c8) {
+    float xin[OC_MAXK + OC_PER - 1][8];
+#pragma unroll
+    for (int i = 0; i < OC_MAXK + OC_PER - 1; ++i) {
+      const long long rr = row0 + i - pad;   // gap rows are zero: no per-tap utterance test is needed
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (i < k + OC_PER - 1 && rr >= 0 && rr < total_rows) u = reinterpret_cast<const uint4*>(x + rr * ld)[c8];
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 f = __bfloat1622float2(h[q]);
-        acc += f.x * ws[j * c + c8 * 8 + 2 * q] + f.y * ws[j * c + c8 * 8 + 2 * q + 1];
+        xin[i][2 * q] = f.x;
+        xin[i][2 * q + 1] = f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < OC_MAXK; ++j) {
+      if (j < k) {
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const float wv = ws[j * c + c8 * 8 + ch];
+#pragma unroll
+          for (int o = 0; o < OC_PER; ++o) acc[o] += xin[o + j][ch] * wv;
+        }
       }
     }
   }
-  const long long t = row - static_cast<long long>(L.seg_start[b]) * rate;
-  wave[static_cast<long long>(frame_off[b]) * rate + t] = tanhf(acc);
+#pragma unroll
+  for (int o = 0; o < OC_PER; ++o) {
+    const long long row = row0 + o;
+    if (row >= total_rows) break;
+    const int b = L.frame_seg[static_cast<int>(row / rate)];
+    if (b < 0) continue;
+    const long long t = row - static_cast<long long>(L.seg_start[b]) * rate;
+    wave[static_cast<long long>(frame_off[b]) * rate + t] = tanhf(acc[o]);
+  }
 }
 int output_conv_tanh(const bf16* x, int ld, int c, const float* w, float bias, int k, RowLayout L, int rate,
                      const int* frame_off, float* wave, cudaStream_t s) {
-  JB_REQUIRE(c % 8 == 0 && ld % 8 == 0, -2, "output_conv: C % 8");
+  JB_REQUIRE(c % 8 == 0 && ld % 8 == 0 && k <= OC_MAXK, -2, "output_conv: C % 8, k <= 7");
   const long long total = static_cast<long long>(L.n_rows) * rate;
   if (total == 0) return 0;
-  output_conv_tanh_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, sizeof(float) * k * c, s>>>(
+  const long long threads = (total + OC_PER - 1) / OC_PER;
+  output_conv_tanh_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, sizeof(float) * k * c, s>>>(
       x, ld, c, w, bias, k, L, rate, frame_off, wave, total);
   JB_KERNEL_OK();
   return 0;
