@@ -93,7 +93,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample line: brackets the timed region"""
+        return len(self.lines)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -103,7 +107,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        window = self.lines[first:last] or self.lines[-3:]   # samples taken while the timed steps ran
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -252,14 +257,20 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
                            int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
     if rank == 0:
+        # nvidia-smi needs a moment to produce its first line: keep the GPU under the same load until it does
         sampler.start()
+        t_wait = time.time()
+        while sampler.mark() == 0 and time.time() - t_wait < 5.0:
+            step_device()
+            torch.cuda.synchronize(dev)
     l0 = _lib.launch_count()
+    s0 = sampler.mark()
     ms_dev = timed(step_device, args.steps)
     launches = (_lib.launch_count() - l0) // args.steps
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(s0, sampler.mark()) if rank == 0 else None
 
     # roofline leg: device time of the dominant kernel (tcgen05 conv GEMM, bf16 = HiFi-GAN convolutions)
     mels = [o["feat_gen"] for o in outs]
@@ -322,7 +333,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()

@@ -140,6 +140,23 @@ typedef struct {
 /* impl 0 = tcgen05 kernel (the product kernel), 1 = CUDA-core twin (test-only cross-check) */
 JATTS_API int jatts_op_conv_gemm(const jatts_conv_gemm_args* a, int32_t impl, void* stream);
 
+/* Fused HiFi-GAN residual unit of the narrow MRF stages (C = 32 / 64), the product kernel behind
+ * jatts_hifigan_run for those stages (jatts_b200/csrc/mrf_pair.cu):
+ *   t = lrelu(conv(xa, w1, dilation) + b1);  v = conv(t, w2, 1) + b2 + x [+ accum];  out = lrelu(v * post_scale, out_slope)
+ * with xa = lrelu(x, slope) as stored and x recovered from it. */
+typedef struct {
+  const void* d_xa; int32_t rows, ld, c;
+  const void* d_w1; const void* d_w2;           /* bf16 [taps][n_pad][k_pad] */
+  int32_t taps, n_pad, k_pad, dilation;
+  const float* d_b1; const float* d_b2;
+  float slope;
+  const uint8_t* d_frame_mask; int32_t rate;
+  const void* d_accum; int32_t accum_ld;
+  float post_scale, out_slope;
+  void* d_out; int32_t out_ld;
+} jatts_mrf_pair_args;
+JATTS_API int jatts_op_mrf_pair(const jatts_mrf_pair_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,11 +54,24 @@ class ConvGemmArgs(C.Structure):
     ]
 
 
+class MrfPairArgs(C.Structure):
+    _fields_ = [
+        ("d_xa", C.c_void_p), ("rows", C.c_int32), ("ld", C.c_int32), ("c", C.c_int32),
+        ("d_w1", C.c_void_p), ("d_w2", C.c_void_p),
+        ("taps", C.c_int32), ("n_pad", C.c_int32), ("k_pad", C.c_int32), ("dilation", C.c_int32),
+        ("d_b1", C.c_void_p), ("d_b2", C.c_void_p), ("slope", C.c_float),
+        ("d_frame_mask", C.c_void_p), ("rate", C.c_int32),
+        ("d_accum", C.c_void_p), ("accum_ld", C.c_int32),
+        ("post_scale", C.c_float), ("out_slope", C.c_float),
+        ("d_out", C.c_void_p), ("out_ld", C.c_int32),
+    ]
+
+
 #: every symbol include/jatts_b200.h declares (tests/test_cabi.py checks the library exports them all)
 EXPORTS = (
     "jatts_abi_version", "jatts_last_error", "jatts_launch_count",
     "jatts_fs2_create", "jatts_fs2_destroy", "jatts_fs2_plan", "jatts_fs2_run",
-    "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_op_conv_gemm",
+    "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_op_conv_gemm", "jatts_op_mrf_pair",
     "jatts_profile_begin", "jatts_profile_end", "jatts_debug_set_trace",
 )
 
@@ -85,6 +98,7 @@ def _load():
     lib.jatts_hifigan_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
                                       C.c_void_p]
     lib.jatts_op_conv_gemm.argtypes = [C.POINTER(ConvGemmArgs), C.c_int32, C.c_void_p]
+    lib.jatts_op_mrf_pair.argtypes = [C.POINTER(MrfPairArgs), C.c_void_p]
     lib.jatts_debug_set_trace.argtypes = [C.c_void_p]
     lib.jatts_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int64)]

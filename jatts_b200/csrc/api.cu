@@ -1,5 +1,6 @@
 // C-ABI glue: version / error / launch counter and the op-level test entry point.
 #include "engine_common.cuh"
+#include "mrf_pair.cuh"
 
 using namespace jb;
 
@@ -28,6 +29,24 @@ extern "C" int jatts_op_conv_gemm(const jatts_conv_gemm_args* a, int32_t impl, v
   e.out_act = static_cast<bf16*>(a->d_out_act); e.out_act_slope = a->out_act_slope; e.out_act_ld = a->out_act_ld;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return impl == 0 ? conv_gemm_tc(p, s) : conv_gemm_simt_debug(p, s);
+}
+
+extern "C" int jatts_op_mrf_pair(const jatts_mrf_pair_args* a, void* stream) {
+  JB_REQUIRE(a != nullptr, JATTS_E_INVALID, "op_mrf_pair: null args");
+  MrfPairProblem p{};
+  p.xa = static_cast<const bf16*>(a->d_xa); p.rows = a->rows; p.ld = a->ld; p.c = a->c;
+  p.w1 = static_cast<const bf16*>(a->d_w1); p.w2 = static_cast<const bf16*>(a->d_w2);
+  p.taps = a->taps; p.n_pad = a->n_pad; p.k_pad = a->k_pad; p.dilation = a->dilation;
+  JB_REQUIRE(a->d_b1 && a->d_b2 && a->c > 0 && a->c <= 64, JATTS_E_INVALID, "op_mrf_pair: bad bias / channel count");
+  float hb[2][64];   // the engine keeps host copies of the biases; the test entry fetches them here
+  JB_CUDA_OK(cudaMemcpy(hb[0], a->d_b1, sizeof(float) * a->c, cudaMemcpyDeviceToHost));
+  JB_CUDA_OK(cudaMemcpy(hb[1], a->d_b2, sizeof(float) * a->c, cudaMemcpyDeviceToHost));
+  p.h_b1 = hb[0]; p.h_b2 = hb[1]; p.slope = a->slope;
+  p.frame_mask = a->d_frame_mask; p.rate = a->rate;
+  p.accum = static_cast<const bf16*>(a->d_accum); p.accum_ld = a->accum_ld;
+  p.post_scale = a->post_scale; p.out_slope = a->out_slope;
+  p.out = static_cast<bf16*>(a->d_out); p.out_ld = a->out_ld;
+  return mrf_pair(p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int jatts_profile_begin(void) {

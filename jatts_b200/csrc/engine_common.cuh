@@ -41,6 +41,7 @@ struct ConvW {
   const bf16* hi = nullptr;
   const bf16* lo = nullptr;
   const float* bias = nullptr;
+  const float* h_bias = nullptr;   // optional host copy (owned by the engine), for kernels that take the bias by value
   int taps = 1, n = 0, n_pad = 0, k_pad = 0, block_n = 128;
 };
 

@@ -5,7 +5,10 @@
 // accumulation; LeakyReLU, bias, residual add, the MRF branch mean and the next layer's operand
 // conversion are fused into the epilogues.  ConvTranspose1d(k = 2s, stride s) is a 2-tap polyphase
 // GEMM with N = s * C_out whose epilogue scatters phase q of input row j to output row j*s + q - p.
+#include <cstdlib>
+
 #include "engine_common.cuh"
+#include "mrf_pair.cuh"
 
 using namespace jb;
 
@@ -16,6 +19,7 @@ struct jatts_hifigan {
   ConvW input_conv;
   std::vector<ConvW> ups;
   std::vector<std::vector<std::vector<ConvW>>> c1, c2;  // [stage][block][dilation]
+  std::vector<std::vector<float>> host_bias;            // host copies of the residual-unit biases (ConvW::h_bias)
   const float *out_w, *mel_scale, *mel_shift;
   float out_b = 0.f;
   int hop = 1;
@@ -88,6 +92,20 @@ static int run_conv(const ConvW& w, const bf16* a, int a_cols, const StageIO& io
   return conv_gemm_tc2(p, s);
 }
 
+// One residual unit x + conv(k,1)(lrelu(conv(k,d)(lrelu(x)))) of a narrow stage in one launch (mrf_pair.cu):
+// only lrelu(x) is kept in HBM, the kernel recovers x from it.
+static MrfPairProblem pair_problem(const ConvW& w1, const ConvW& w2, const bf16* xa, int c, const StageIO& io, int dilation,
+                                   float slope) {
+  MrfPairProblem p{};
+  p.xa = xa; p.rows = static_cast<int>(io.rows); p.ld = c; p.c = c;
+  p.w1 = w1.hi; p.w2 = w2.hi; p.taps = w1.taps; p.n_pad = w1.n_pad; p.k_pad = w1.k_pad; p.dilation = dilation;
+  p.h_b1 = w1.h_bias; p.h_b2 = w2.h_bias; p.slope = slope;
+  p.frame_mask = io.mask; p.rate = io.rate;
+  p.post_scale = 1.f; p.out_slope = slope;
+  p.out_ld = c;
+  return p;
+}
+
 }  // namespace jb
 
 extern "C" int jatts_hifigan_create(const jatts_hifigan_config* cfg, const jatts_tensor* weights, int32_t n_weights,
@@ -130,6 +148,14 @@ extern "C" int jatts_hifigan_create(const jatts_hifigan_config* cfg, const jatts
         const std::string p = "rb" + std::to_string(i) + "_" + std::to_string(j);
         if ((rc = load_conv(h->wt, p + ".c1_" + std::to_string(d), k, co, co, false, true, co, &h->c1[i][j][d]))) return fail(rc);
         if ((rc = load_conv(h->wt, p + ".c2_" + std::to_string(d), k, co, co, false, true, co, &h->c2[i][j][d]))) return fail(rc);
+        for (ConvW* w : {&h->c1[i][j][d], &h->c2[i][j][d]}) {
+          h->host_bias.emplace_back(co);
+          if (cudaMemcpy(h->host_bias.back().data(), w->bias, sizeof(float) * co, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_last_error("cudaMemcpy(bias) failed");
+            return fail(JATTS_E_CUDA);
+          }
+          w->h_bias = h->host_bias.back().data();   // the inner vector's buffer does not move when host_bias grows
+        }
         // the gap between utterances must cover the widest receptive field at this rate
         if ((k - 1) / 2 * cfg->resblock_dilations[j][d] > kGapRows * r) {
           set_last_error("dilated receptive field exceeds the inter-utterance gap");
@@ -209,6 +235,18 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
     const int sc = c.upsample_scales[i];
     const int co = h->chans[i];
     const StageIO in_io = io;
+    // narrow stages (HBM bound when unfused): one launch per residual unit, lrelu(x) is the only stored tensor
+    static const bool no_fuse = getenv("JATTS_B200_NO_FUSE") != nullptr;
+    bool fused = !no_fuse && (co == 32 || co == 64);
+    if (fused) {
+      StageIO probe{h->mask, h->rate[i], static_cast<long long>(hl.n_rows) * h->rate[i]};
+      for (int j = 0; j < c.n_resblocks && fused; ++j)
+        for (int d = 0; d < c.n_dilations && fused; ++d) {
+          MrfPairProblem pp = pair_problem(h->c1[i][j][d], h->c2[i][j][d], h->xa0, co, probe, c.resblock_dilations[j][d], slope);
+          pp.out = h->x;
+          fused = h->c1[i][j][d].taps == h->c2[i][j][d].taps && mrf_pair_eligible(pp);
+        }
+    }
     io.rate = h->rate[i];
     io.rows = static_cast<long long>(hl.n_rows) * io.rate;
     const int nxt = cur ^ 1;
@@ -236,7 +274,7 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
         p.out_view_rows = static_cast<int>((io.rows - first + sc - 1) / sc);
         ConvGemmEpilogue e{};
         e.bias = w.bias; e.scale = 1.f; e.post_scale = 1.f;
-        e.out_hi = h->x0 + first * co; e.out_bf_ld = co;
+        if (!fused) { e.out_hi = h->x0 + first * co; e.out_bf_ld = co; }
         e.out_act = h->xa0 + first * co; e.out_act_slope = slope; e.out_act_ld = co;
         p.ep = e;
         JB_REQUIRE(conv_gemm_tc2_eligible(p), JATTS_E_UNSUPPORTED, "transposed-conv phase not eligible for the TMA kernel");
@@ -245,7 +283,27 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
     }
     const bool last_stage = i == c.n_upsamples - 1;
     const float next_slope = last_stage ? 0.01f : slope;  // torch.nn.LeakyReLU() default before output_conv
-    for (int j = 0; j < c.n_resblocks; ++j) {
+    for (int j = 0; j < c.n_resblocks && fused; ++j) {
+      const bf16* in = h->xa0;
+      for (int d = 0; d < c.n_dilations; ++d) {
+        MrfPairProblem pp = pair_problem(h->c1[i][j][d], h->c2[i][j][d], in, co, io, c.resblock_dilations[j][d], slope);
+        if (d + 1 < c.n_dilations) {
+          pp.out = (d & 1) ? h->xa : h->x;   // ping-pong: other CTAs still read the input's halo rows
+        } else {
+          // branch output: accumulate the sum over residual blocks (in place, a tile reads its own rows before
+          // storing them); the last block emits the next layer's operand leaky_relu(mean) directly
+          if (j > 0) { pp.accum = h->sum; pp.accum_ld = co; }
+          if (j + 1 < c.n_resblocks) {
+            pp.out = h->sum; pp.out_slope = 1.f;
+          } else {
+            pp.out = h->y[nxt]; pp.post_scale = 1.0f / c.n_resblocks; pp.out_slope = next_slope;
+          }
+        }
+        JB_PROPAGATE(mrf_pair(pp, s));
+        in = pp.out;
+      }
+    }
+    for (int j = 0; j < c.n_resblocks && !fused; ++j) {
       const bf16* x_res = h->x0;
       const bf16* xa = h->xa0;
       for (int d = 0; d < c.n_dilations; ++d) {

@@ -51,11 +51,18 @@ __device__ __forceinline__ uint64_t global_ns() {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_ns();
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_ns() - t0 > 4000000000ull) {  // 4 s
-      printf("jatts_b200: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
-      __trap();
+    // the timer is only consulted every 4096 polls: %globaltimer reads are slow and the poll loop of a waiting
+    // warp must not take issue slots from the warps doing the work
+    if ((++spins & 0xFFFu) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {  // 4 s
+        printf("jatts_b200: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
     }
   }
 }
