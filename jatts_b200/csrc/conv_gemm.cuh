@@ -23,6 +23,7 @@ struct ConvGemmEpilogue {
   float scale;              // v = act(acc + bias) * scale
   const float* res_f32;     // v += res_f32[row*res_ld + n]
   const bf16* res_bf16;     // v += res_bf16[row*res_ld + n]
+  float res_inv_slope;      // != 0: res_bf16 holds LeakyReLU(x, s) and x is recovered as r >= 0 ? r : r * res_inv_slope (= 1/s)
   int res_ld;
   const float* accum_in;    // v += accum_in[row*out_f32_ld + n]   (fp32 running sum)
   const bf16* accum_bf16;   // v += accum_bf16[row*res_ld + n]     (MRF branch sum kept in bf16)

@@ -551,6 +551,7 @@ int conv_gemm_tc(const ConvGemmProblem& p, cudaStream_t stream) {
   JB_PROPAGATE(validate(p));
   static const bool no_tc2 = getenv("JATTS_B200_NO_TC2") != nullptr;  // A/B switch for profiling
   if (!no_tc2 && conv_gemm_tc2_eligible(p)) return conv_gemm_tc2(p, stream);
+  JB_REQUIRE(p.ep.res_inv_slope == 0.f, -1, "res_inv_slope is only implemented by the TMA-epilogue kernel");
   static const bool no_tc3 = getenv("JATTS_B200_NO_TC3") != nullptr;
   if (!no_tc3 && conv_gemm_tc3_eligible(p)) return conv_gemm_tc3(p, stream);
   const bool split = p.a_lo != nullptr;

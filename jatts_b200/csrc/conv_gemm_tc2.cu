@@ -36,6 +36,8 @@ struct KernelParams2 {
   int tap_off0, tap_stride;
   int m_rows;
   int num_m_tiles, num_n_tiles;
+  int cl;           // CTAs per cluster sharing the streamed weight tiles by TMA multicast (HALO mode), else 1
+  int num_groups;   // ceil(num_m_tiles / cl) * num_n_tiles: a cluster walks groups of cl M tiles x one N tile
   const uint8_t* frame_mask;
   int rate;
   const float* bias;
@@ -43,6 +45,7 @@ struct KernelParams2 {
   float slope;
   float post_scale;
   float out1_slope;
+  float res_inv_slope;   // != 0: the residual tensor stores LeakyReLU(x); recover x before adding
   int has_res, has_acc, has_out0, has_out1;
   int halo_rows;    // HALO/RESIDENT: rows of the activation box (128 + (taps-1)*tap_stride, padded to 8)
   int ep_entries;   // epilogue ring depth (2..8)
@@ -129,6 +132,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
 template <int BLOCK_N, int KCH, int MODE>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                     const __grid_constant__ CUtensorMap tm_bm,
                      const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_acc,
                      const __grid_constant__ CUtensorMap tm_out0, const __grid_constant__ CUtensorMap tm_out1,
                      const __grid_constant__ KernelParams2 P) {
@@ -160,7 +164,13 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = P.num_m_tiles * P.num_n_tiles;
+  // tile schedule: cluster `cid` takes groups cid, cid + ncl, ...; CTA `rank` of the cluster owns M tile
+  // (grp / num_n_tiles) * cl + rank of the group (past the end: loads zero-fill, stores clip)
+  const int cl = P.cl;
+  const int rank = static_cast<int>(blockIdx.x) % cl;
+  const int cid = static_cast<int>(blockIdx.x) / cl;
+  const int ncl = static_cast<int>(gridDim.x) / cl;
+  const uint16_t cl_mask = static_cast<uint16_t>((1u << cl) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -171,7 +181,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (P.has_out1) tma_prefetch_desc(&tm_out1);
     for (int i = 0; i < NB; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MODE == MODE_HALO ? cl : 1);   // multicast weight stage: freed by every CTA of the cluster
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&afull_bar[i], 1);
@@ -198,6 +208,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   for (int i = threadIdx.x; i < P.n_pad && i < C::BIAS_BYTES / 4; i += kThreads2) bias_s[i] = P.bias ? P.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();   // peers' mbarriers are initialised before any multicast load / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -213,9 +224,9 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       }
       const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * C::KROWB;
       Ring rs(0, STAGES), ra(0, C::A_STAGES), rb(0, C::B_STAGES);
-      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
-        const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
-        const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+      for (int grp = cid, seq = 0; grp < P.num_groups; grp += ncl, ++seq) {
+        const int m0 = ((grp / P.num_n_tiles) * cl + rank) * BLOCK_M2;
+        const int n0 = (grp % P.num_n_tiles) * BLOCK_N;
         if (MODE == MODE_STREAM) {
           for (int tap = 0; tap < P.taps; ++tap) {
             const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
@@ -240,7 +251,14 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
               for (int tap = 0; tap < P.taps; ++tap) {
                 mbar_wait(&empty_bar[rb.idx], rb.phase ^ 1);
                 mbar_expect_tx(&full_bar[rb.idx], C::B_BYTES);
-                tma_load_2d(&tm_b, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride + n0);
+                if (cl == 1) {
+                  tma_load_2d(&tm_b, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride + n0);
+                } else {
+                  // this CTA fetches rows [rank, rank + 1) * BLOCK_N / cl of the weight tile for the whole cluster
+                  const int slice = BLOCK_N / cl;
+                  tma_load_2d_mc(&tm_bm, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES + rank * slice * C::KROWB, kc * KCH,
+                                 P.w_row0 + tap * P.w_tap_stride + n0 + rank * slice, cl_mask);
+                }
                 rb.next();
               }
             }
@@ -263,7 +281,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       constexpr uint32_t desc_lo0 = 1u << 16;
       constexpr uint32_t desc_hi = static_cast<uint32_t>((8 * KCH * 2) >> 4) | (1u << 14) | (static_cast<uint32_t>(KCH == 64 ? 2 : 4) << 29);
       bool weights_ready = MODE != MODE_RESIDENT;
-      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+      for (int grp = cid, seq = 0; grp < P.num_groups; grp += ncl, ++seq) {
         const int acc = seq & 1;   // accumulator (and epilogue group) of this tile
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
         mbar_wait(&tempty_bar[acc], ((seq >> 1) & 1) ^ 1);
@@ -319,7 +337,10 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k)
                 tc_mma_bf16_lohi(tmem_d, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-              if (MODE == MODE_HALO) tc_commit(&empty_bar[bs]);
+              if (MODE == MODE_HALO) {
+                if (cl == 1) tc_commit(&empty_bar[bs]);
+                else tc_commit_mc(&empty_bar[bs], cl_mask);
+              }
             }
             tc_commit(&aempty_bar[as]);
           }
@@ -333,10 +354,10 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (elect_one()) {
       const uint32_t bytes = (P.has_res ? C::SLAB_BYTES : 0) + (P.has_acc ? C::SLAB_BYTES : 0);
       Ring rg0(0, E / 2), rg1(E / 2, E / 2);   // the two epilogue groups' halves of the ring
-      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+      for (int grp = cid, seq = 0; grp < P.num_groups; grp += ncl, ++seq) {
         Ring& re = (seq & 1) ? rg1 : rg0;
-        const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
-        const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+        const int m0 = ((grp / P.num_n_tiles) * cl + rank) * BLOCK_M2;
+        const int n0 = (grp % P.num_n_tiles) * BLOCK_N;
         for (int s = 0; s < C::N_SLABS; ++s) {
           const int e = re.idx;
           mbar_wait(&epempty_bar[e], re.phase ^ 1);
@@ -360,10 +381,10 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       int hist0 = 0, hist1 = 0;   // entries of the two most recently committed store groups
       const int depth = P.store_depth;   // older groups kept in flight behind the one just committed (0..2)
       Ring rg0(0, E / 2), rg1(E / 2, E / 2);
-      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+      for (int grp = cid, seq = 0; grp < P.num_groups; grp += ncl, ++seq) {
         Ring& re = (seq & 1) ? rg1 : rg0;
-        const int m0 = (tile / P.num_n_tiles) * BLOCK_M2;
-        const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+        const int m0 = ((grp / P.num_n_tiles) * cl + rank) * BLOCK_M2;
+        const int n0 = (grp % P.num_n_tiles) * BLOCK_N;
         for (int s = 0; s < C::N_SLABS; ++s) {
           const int e = re.idx;
           mbar_wait(&ready_bar[e], re.phase);  // the 128 threads of the tile's epilogue group wrote + fenced this slab
@@ -405,20 +426,20 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     Ring re(pipe * (E / 2), E / 2);
     // row validity of this group's NEXT tile is fetched while the current one is processed; the raw byte
     // stays in a register and is only compared one tile later, so the load is off the critical path
-    auto row_valid = [&](int tile) -> unsigned {
-      if (tile >= num_tiles) return 0u;
-      const int row = (tile / P.num_n_tiles) * BLOCK_M2 + row_in_tile;
+    auto row_valid = [&](int grp) -> unsigned {
+      if (grp >= P.num_groups) return 0u;
+      const int row = ((grp / P.num_n_tiles) * cl + rank) * BLOCK_M2 + row_in_tile;
       if (row >= P.m_rows) return 0u;
       const long long orow = static_cast<long long>(row) * P.mask_mul + P.mask_add;
       if (orow < 0 || orow >= P.out_rows) return 0u;
       return P.frame_mask ? static_cast<unsigned>(__ldg(P.frame_mask + orow / P.rate)) : 1u;
     };
-    unsigned valid_next = row_valid(blockIdx.x + pipe * gridDim.x);
-    for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+    unsigned valid_next = row_valid(cid + pipe * ncl);
+    for (int grp = cid, seq = 0; grp < P.num_groups; grp += ncl, ++seq) {
       if ((seq & 1) != pipe) continue;
-      const int n0 = (tile % P.num_n_tiles) * BLOCK_N;
+      const int n0 = (grp % P.num_n_tiles) * BLOCK_N;
       const float row_scale = valid_next != 0u ? P.post_scale : 0.0f;
-      valid_next = row_valid(tile + 2 * gridDim.x);
+      valid_next = row_valid(grp + 2 * ncl);
       if (warp == 4 && lane == 0) JB_TRACE(4, 3, seq);
       mbar_wait(&tfull_bar[acc], n_done & 1);
       ++n_done;
@@ -466,7 +487,11 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(h[j]);
+              float2 f = __bfloat1622float2(h[j]);
+              if (P.res_inv_slope != 0.f) {
+                f.x = f.x >= 0.f ? f.x : f.x * P.res_inv_slope;
+                f.y = f.y >= 0.f ? f.y : f.y * P.res_inv_slope;
+              }
               v[2 * j] += f.x; v[2 * j + 1] += f.y;
             }
           }
@@ -506,6 +531,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -523,6 +549,7 @@ bool conv_gemm_tc2_eligible(const ConvGemmProblem& p) {
   if (!(e.act == ACT_NONE || e.act == ACT_LRELU)) return false;
   if (e.res_f32 || e.accum_in || e.out_f32 || e.out_lo) return false;
   if (e.scale != 1.0f) return false;
+  if (e.res_inv_slope != 0.f && !e.res_bf16) return false;
   const bool phase = p.w_tap_stride != 0;
   if ((!phase && p.n != p.n_pad) || p.n > 512 || p.n % p.block_n != 0) return false;
   if (!phase && p.out_rows != p.m_rows) return false;
@@ -540,13 +567,21 @@ template <int BLOCK_N, int KCH, int MODE>
 static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   using C = Cfg2<BLOCK_N, KCH, MODE>;
   const ConvGemmEpilogue& e = p.ep;
-  CUtensorMap ta, tb, tres, tacc, to0, to1;
+  CUtensorMap ta, tb, tbm, tres, tacc, to0, to1;
   const int a_cols = p.a_cols > 0 ? p.a_cols : p.k_pad;
   const int k_chunks = ceil_div(a_cols, KCH);   // channel padding beyond a_cols is all-zero: skip it
   const int halo_rows = round_up(BLOCK_M2 + (p.taps - 1) * p.tap_stride, 8);
   JB_PROPAGATE(make_tmap(&ta, p.a_hi, p.a_rows, a_cols, p.a_ld, MODE == MODE_STREAM ? BLOCK_M2 : halo_rows, KCH));
   const long long w_rows = p.w_tap_stride != 0 ? static_cast<long long>(p.w_rows_total) : static_cast<long long>(p.taps) * p.n_pad;
   JB_PROPAGATE(make_tmap(&tb, p.w_hi, w_rows, p.k_pad, p.k_pad, BLOCK_N, KCH));
+  // HALO mode streams every weight tile once per M tile from L2 (measured: ~7.5 TB/s aggregate, the bound of the
+  // C = 128 / 256 stages): CTAs of a cluster work on neighbouring M tiles in lockstep and share each weight tile
+  // through TMA multicast, every CTA fetching 1/cl of it.
+  static const int env_cl = getenv("JATTS_B200_TC2_CL") ? atoi(getenv("JATTS_B200_TC2_CL")) : 1;
+  int cl = 1;
+  if (MODE == MODE_HALO && (env_cl == 2 || env_cl == 4) && ceil_div(p.m_rows, BLOCK_M2) >= 2 * env_cl) cl = env_cl;
+  tbm = tb;
+  if (cl > 1) JB_PROPAGATE(make_tmap(&tbm, p.w_hi, w_rows, p.k_pad, p.k_pad, BLOCK_N / cl, KCH));
   tres = tacc = to0 = to1 = ta;
   if (e.res_bf16) JB_PROPAGATE(make_tmap(&tres, e.res_bf16, p.m_rows, p.n, e.res_ld, BLOCK_M2, C::SLAB));
   if (e.accum_bf16) JB_PROPAGATE(make_tmap(&tacc, e.accum_bf16, p.m_rows, p.n, e.res_ld, BLOCK_M2, C::SLAB));
@@ -563,6 +598,8 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.m_rows = p.m_rows;
   kp.num_m_tiles = ceil_div(p.m_rows, BLOCK_M2);
   kp.num_n_tiles = (p.w_tap_stride != 0 ? p.n : p.n_pad) / BLOCK_N;
+  kp.cl = cl;
+  kp.num_groups = ceil_div(kp.num_m_tiles, cl) * kp.num_n_tiles;
   kp.frame_mask = p.frame_mask;
   kp.rate = p.rate > 0 ? p.rate : 1;
   kp.bias = e.bias;
@@ -570,6 +607,7 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.slope = e.slope;
   kp.post_scale = e.post_scale;
   kp.out1_slope = e.out_act_slope;
+  kp.res_inv_slope = e.res_inv_slope;
   kp.has_res = e.res_bf16 != nullptr;
   kp.has_acc = e.accum_bf16 != nullptr;
   kp.has_out0 = e.out_hi != nullptr;
@@ -602,16 +640,47 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
     JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_bytes = smem_bytes;
   }
-  const int tiles = kp.num_m_tiles * kp.num_n_tiles;
-  if (tiles == 0) return 0;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (kp.num_groups == 0) return 0;
+  int max_clusters = num_sms() / cl;
+  if (cl > 2) {
+    // clusters of 4 must fit inside a GPC: ask how many can be resident with this much shared memory
+    static int cached[8] = {0};
+    if (cached[cl] == 0) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(num_sms() / cl * cl);
+      qc.blockDim = dim3(kThreads2);
+      qc.dynamicSmemBytes = smem_bytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = cl; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int n = 0;
+      JB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &qc));
+      cached[cl] = n > 0 ? n : 1;
+    }
+    if (cached[cl] < max_clusters) max_clusters = cached[cl];
+  }
+  const int grid = (kp.num_groups < max_clusters ? kp.num_groups : max_clusters) * cl;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventCreate(&e0));
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  kern<<<grid, kThreads2, smem_bytes, stream>>>(ta, tb, tres, tacc, to0, to1, kp);
+  if (cl == 1) {
+    kern<<<grid, kThreads2, smem_bytes, stream>>>(ta, tb, tbm, tres, tacc, to0, to1, kp);
+  } else {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads2);
+    lc.dynamicSmemBytes = smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = cl; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    lc.attrs = la; lc.numAttrs = 1;
+    JB_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ta, tb, tbm, tres, tacc, to0, to1, kp));
+  }
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));

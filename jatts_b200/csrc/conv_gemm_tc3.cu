@@ -401,7 +401,7 @@ bool conv_gemm_tc3_eligible(const ConvGemmProblem& p) {
   const ConvGemmEpilogue& e = p.ep;
   if (!p.a_lo || !p.w_lo || p.up_s > 0 || p.block_n != BN || p.w_tap_stride != 0) return false;
   if (!(e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_TANH || e.act == ACT_GLU)) return false;
-  if (e.res_bf16 || e.accum_in || e.accum_bf16 || e.out_act) return false;
+  if (e.res_bf16 || e.accum_in || e.accum_bf16 || e.out_act || e.res_inv_slope != 0.f) return false;
   if ((e.out_hi != nullptr) != (e.out_lo != nullptr)) return false;
   if (e.post_scale != 1.0f) return false;
   if (p.n_pad > BIAS_BYTES / 4 || p.out_rows != p.m_rows) return false;

@@ -27,7 +27,7 @@ struct jatts_hifigan {
 
   Arena arena;
   int cap_rows = 0, cap_utt = 0;
-  bf16 *mel, *x0, *xa0, *x, *xa, *t, *y[2], *sum;
+  bf16 *mel, *xa0, *x, *xa, *t, *y[2], *sum;   // xa0 / x / xa hold lrelu(x) of the stage input and of the units' outputs
   uint8_t* mask;
   int *seg, *d_small = nullptr, *h_small = nullptr;
   cudaEvent_t staged = nullptr;
@@ -52,13 +52,13 @@ static int ensure_workspace(jatts_hifigan* h, int rows, int n_utt) {
   size_t per_row = static_cast<size_t>(c.channels);  // stage input of stage 0: [rows, channels]
   for (size_t i = 0; i < h->rate.size(); ++i) per_row = std::max(per_row, static_cast<size_t>(h->rate[i]) * h->chans[i]);
   const size_t in_pad = round_up(c.in_channels, 64);
-  size_t bytes = Arena::padded(2 * R * in_pad) + 8 * Arena::padded(2 * R * per_row) +
+  size_t bytes = Arena::padded(2 * R * in_pad) + 7 * Arena::padded(2 * R * per_row) +
                  Arena::padded(R) + Arena::padded(4 * R);
   JB_PROPAGATE(h->arena.reserve(bytes));
   Arena& a = h->arena;
   a.reset();
   h->mel = a.take<bf16>(R * in_pad);
-  h->x0 = a.take<bf16>(R * per_row); h->xa0 = a.take<bf16>(R * per_row);
+  h->xa0 = a.take<bf16>(R * per_row);
   h->x = a.take<bf16>(R * per_row); h->xa = a.take<bf16>(R * per_row);
   h->t = a.take<bf16>(R * per_row);
   h->y[0] = a.take<bf16>(R * per_row); h->y[1] = a.take<bf16>(R * per_row);
@@ -82,6 +82,8 @@ static int run_conv(const ConvW& w, const bf16* a, int a_cols, const StageIO& io
   p.w_hi = w.hi; p.w_lo = nullptr; p.taps = w.taps; p.n_pad = w.n_pad; p.k_pad = w.k_pad;
   p.tap_off0 = -((w.taps - 1) / 2) * dilation; p.tap_stride = dilation;
   p.n = w.n; p.m_rows = static_cast<int>(io.rows); p.block_n = w.block_n;
+  static const int bn_cap = getenv("JATTS_B200_BN_CAP") ? atoi(getenv("JATTS_B200_BN_CAP")) : 128;
+  if (w.taps > 1 && p.block_n > bn_cap && w.n_pad % bn_cap == 0) p.block_n = bn_cap;
   p.frame_mask = io.mask; p.rate = io.rate; p.out_rows = static_cast<int>(io.rows);
   ep.bias = w.bias;
   if (ep.scale == 0.f) ep.scale = 1.f;
@@ -274,7 +276,6 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
         p.out_view_rows = static_cast<int>((io.rows - first + sc - 1) / sc);
         ConvGemmEpilogue e{};
         e.bias = w.bias; e.scale = 1.f; e.post_scale = 1.f;
-        if (!fused) { e.out_hi = h->x0 + first * co; e.out_bf_ld = co; }
         e.out_act = h->xa0 + first * co; e.out_act_slope = slope; e.out_act_ld = co;
         p.ep = e;
         JB_REQUIRE(conv_gemm_tc2_eligible(p), JATTS_E_UNSUPPORTED, "transposed-conv phase not eligible for the TMA kernel");
@@ -304,16 +305,20 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
       }
     }
     for (int j = 0; j < c.n_resblocks && !fused; ++j) {
-      const bf16* x_res = h->x0;
+      // wide stages: two launches per residual unit.  Only lrelu(x) is stored (as in the fused path): conv2's
+      // epilogue recovers x from it for the residual add, so a unit moves 5 activation tensors instead of 6
+      // and its epilogue ring entries are one slab wide.
       const bf16* xa = h->xa0;
       for (int d = 0; d < c.n_dilations; ++d) {
         ConvGemmEpilogue e1{};
         e1.act = ACT_LRELU; e1.slope = slope; e1.out_hi = h->t; e1.out_bf_ld = co;
         JB_PROPAGATE(run_conv(h->c1[i][j][d], xa, co, io, c.resblock_dilations[j][d], e1, s));
         ConvGemmEpilogue e2{};
-        e2.res_bf16 = x_res; e2.res_ld = co;
+        e2.res_bf16 = xa; e2.res_ld = co; e2.res_inv_slope = 1.0f / slope;
         if (d + 1 < c.n_dilations) {
-          e2.out_hi = h->x; e2.out_bf_ld = co; e2.out_act = h->xa; e2.out_act_slope = slope; e2.out_act_ld = co;
+          bf16* out = (d & 1) ? h->xa : h->x;
+          e2.out_act = out; e2.out_act_slope = slope; e2.out_act_ld = co;
+          xa = out;
         } else {
           // branch output: accumulate the mean over residual blocks; the last block emits the next
           // layer's operand leaky_relu(mean) directly
@@ -326,8 +331,6 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
           }
         }
         JB_PROPAGATE(run_conv(h->c2[i][j][d], h->t, co, io, 1, e2, s));
-        x_res = h->x;
-        xa = h->xa;
       }
     }
     cur = nxt;
