@@ -2,7 +2,12 @@
 // operand pairs (x ~= hi + lo*2^-11, common.cuh::split_op16) on tcgen05 tensor cores, with the TMA-staged
 // epilogue of conv_gemm_tc2.cu.
 //
-//   warp 0   TMA producer: per K block one stage = A_hi, A_lo [128 x 64] + B_hi, B_lo [128 x 64] (64 KB)
+//   warp 0   TMA producer.  Activations: per 64-wide K chunk ONE slab pair A_hi, A_lo of [128 + (taps-1)*stride
+//            rows x 64] that serves every tap (tap t is an MMA whose A descriptor starts t*stride rows into
+//            the slab), weights: per (K chunk, tap) one B_hi, B_lo [128 x 64] pair.  The kernel is bound by
+//            the bytes an SM can take in (~40 B/clk measured across three kernels): loading the
+//            activations once per K chunk instead of once per tap takes a k = 3 convolution from 85 to 56
+//            bytes per MMA clock.
 //   warp 1   MMA issuer: per K step hi*hi -> main accumulator, lo*hi + hi*lo -> correction accumulator
 //            (both in TMEM, fp32); accumulation runs in CHAINS of 8 K blocks because tcgen05 truncates when
 //            it adds into TMEM (measured bias 1.7e-5 after 288 MMAs) -- chains ping-pong between
@@ -34,16 +39,21 @@ constexpr int BK = 64;        // fp16 elements per K block = one 128-byte swizzl
 constexpr int UK = 16;
 constexpr int kThreads3 = 256;
 constexpr int CHUNK = 8;      // K blocks per accumulation chain
-constexpr int STAGES = 2;
-constexpr int OP_BYTES = BM * BK * 2;          // 16 KB: one operand tile (A or B, hi or lo)
-constexpr int STAGE_BYTES = 4 * OP_BYTES;      // A_hi | B_hi | A_lo | B_lo
+constexpr int A_STAGES = 2;
+constexpr int MAX_B_STAGES = 3;
+constexpr int OP_BYTES = BM * BK * 2;          // 16 KB: one weight tile (hi or lo)
+constexpr int B_STAGE_BYTES = 2 * OP_BYTES;    // B_hi | B_lo
+constexpr int A_SLAB_ROWS = 144;               // 128 + halo of the taps (<= 16 rows)
+constexpr int A_OP_BYTES = A_SLAB_ROWS * BK * 2;   // 18 KB (multiple of 1024)
+constexpr int A_STAGE_BYTES = 2 * A_OP_BYTES;  // A_hi | A_lo
 constexpr int SLAB = 32;                        // columns per epilogue slab
 constexpr int F32_SLAB_BYTES = BM * SLAB * 4;   // 16 KB, 128-byte rows (SWIZZLE_128B)
 constexpr int H16_SLAB_BYTES = BM * SLAB * 2;   // 8 KB, 64-byte rows (SWIZZLE_64B)
 constexpr int MAX_ENTRIES = 6;
 constexpr int BIAS_BYTES = 8192;                // n_pad <= 2048
 constexpr int BAR_BYTES = 1024;
-constexpr int SMEM_FIXED = STAGES * STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+constexpr int SMEM_MISC = BIAS_BYTES + BAR_BYTES + 1024;
+constexpr int smem_fixed(int b_stages) { return A_STAGES * A_STAGE_BYTES + b_stages * B_STAGE_BYTES + SMEM_MISC; }
 constexpr int TMEM_COLS = 512;                  // 2 buffers x (main 128 | corr 128)
 
 struct Params3 {
@@ -58,6 +68,8 @@ struct Params3 {
   float scale;
   int has_res, has_f32, has_split;
   int entries, entry_bytes;
+  int b_stages;     // weight ring depth (2..3)
+  int halo_rows;    // rows of the activation slab: 128 + (taps-1)*tap_stride rounded up to 8
   long long* trace;
 };
 
@@ -95,12 +107,15 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                       const __grid_constant__ Params3 P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* b_ring = smem + A_STAGES * A_STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(b_ring + P.b_stages * B_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + BIAS_BYTES);
   uint8_t* ep_base = reinterpret_cast<uint8_t*>(bars) + BAR_BYTES;   // 1024-aligned
-  uint64_t* full_bar = bars;                       // [STAGES]
-  uint64_t* empty_bar = full_bar + STAGES;         // [STAGES]
-  uint64_t* tfull_bar = empty_bar + STAGES;        // [2]
+  uint64_t* full_bar = bars;                       // [MAX_B_STAGES]  weight ring
+  uint64_t* empty_bar = full_bar + MAX_B_STAGES;   // [MAX_B_STAGES]
+  uint64_t* afull_bar = empty_bar + MAX_B_STAGES;  // [A_STAGES]      activation slabs
+  uint64_t* aempty_bar = afull_bar + A_STAGES;     // [A_STAGES]
+  uint64_t* tfull_bar = aempty_bar + A_STAGES;     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint64_t* epfull_bar = tempty_bar + 2;           // [MAX_ENTRIES]
   uint64_t* epempty_bar = epfull_bar + MAX_ENTRIES;
@@ -120,7 +135,8 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
     tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < MAX_B_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     for (int i = 0; i < MAX_ENTRIES; ++i) {
       mbar_init(&epfull_bar[i], 1);
@@ -148,23 +164,27 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * BK * 2;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / P.num_n_tiles) * BM;
         const int n0 = (tile % P.num_n_tiles) * BN;
-        for (int tap = 0; tap < P.taps; ++tap) {
-          const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
-          const int brow = tap * P.n_pad + n0;
-          for (int kc = 0; kc < P.k_chunks; ++kc) {
+        for (int kc = 0; kc < P.k_chunks; ++kc) {
+          mbar_wait(&aempty_bar[as], aphase ^ 1);
+          uint8_t* a = smem + as * A_STAGE_BYTES;
+          mbar_expect_tx(&afull_bar[as], 2 * a_bytes);
+          tma_load_2d(&tm_a_hi, &afull_bar[as], a, kc * BK, m0 + P.tap_off0);
+          tma_load_2d(&tm_a_lo, &afull_bar[as], a + A_OP_BYTES, kc * BK, m0 + P.tap_off0);
+          if (++as == A_STAGES) { as = 0; aphase ^= 1; }
+          for (int tap = 0; tap < P.taps; ++tap) {
+            const int brow = tap * P.n_pad + n0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* s = smem + stage * STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(&tm_a_hi, &full_bar[stage], s, kc * BK, arow);
-            tma_load_2d(&tm_b_hi, &full_bar[stage], s + OP_BYTES, kc * BK, brow);
-            tma_load_2d(&tm_a_lo, &full_bar[stage], s + 2 * OP_BYTES, kc * BK, arow);
-            tma_load_2d(&tm_b_lo, &full_bar[stage], s + 3 * OP_BYTES, kc * BK, brow);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            uint8_t* b = b_ring + stage * B_STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], B_STAGE_BYTES);
+            tma_load_2d(&tm_b_hi, &full_bar[stage], b, kc * BK, brow);
+            tma_load_2d(&tm_b_lo, &full_bar[stage], b + OP_BYTES, kc * BK, brow);
+            if (++stage == P.b_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -173,39 +193,51 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BM, BN, /*is_bf16=*/false);   // fp16 operands
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
       int buf = 0;
       uint32_t buf_phase = 0;
       for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
         JB_TRACE3(1, 0, seq);
-        int it = 0;
-        while (it < k_iters) {
-          const int it_begin = it;
-          const int it_end = it + CHUNK < k_iters ? it + CHUNK : k_iters;
-          mbar_wait(&tempty_bar[buf], buf_phase ^ 1);
+        int it = 0;          // (K chunk, tap) steps issued for this tile
+        int in_chain = 0;    // steps accumulated into the current chain
+        uint32_t tmem_d = 0, tmem_c = 0;
+        for (int kc = 0; kc < P.k_chunks; ++kc) {
+          mbar_wait(&afull_bar[as], aphase);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 2 * BN);   // main
-          const uint32_t tmem_c = tmem_d + BN;                                        // correction
-          for (; it < it_end; ++it) {
+          const uint32_t sa = smem_u32(smem + as * A_STAGE_BYTES);
+          for (int tap = 0; tap < P.taps; ++tap, ++it) {
+            if (in_chain == 0) {
+              mbar_wait(&tempty_bar[buf], buf_phase ^ 1);
+              tc_fence_after();
+              tmem_d = tmem_base + static_cast<uint32_t>(buf * 2 * BN);   // main
+              tmem_c = tmem_d + BN;                                        // correction
+            }
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t da_hi = desc128(sa), db_hi = desc128(sa + OP_BYTES);
-            const uint64_t da_lo = desc128(sa + 2 * OP_BYTES), db_lo = desc128(sa + 3 * OP_BYTES);
+            const uint32_t sb = smem_u32(b_ring + stage * B_STAGE_BYTES);
+            // tap t reads activation rows [t*stride, t*stride + 128) of the slab (row-shifted descriptor start)
+            const uint32_t a_tap = sa + static_cast<uint32_t>(tap * P.tap_stride) * (BK * 2);
+            const uint64_t da_hi = desc128(a_tap), db_hi = desc128(sb);
+            const uint64_t da_lo = desc128(a_tap + A_OP_BYTES), db_lo = desc128(sb + OP_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
               const uint64_t koff = static_cast<uint64_t>((k * UK * 2) >> 4);
-              const uint32_t first = (it != it_begin || k != 0) ? 1u : 0u;
+              const uint32_t first = (in_chain != 0 || k != 0) ? 1u : 0u;
               tc_mma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, first);
               tc_mma_bf16(tmem_c, da_lo + koff, db_hi + koff, idesc, first);
               tc_mma_bf16(tmem_c, da_hi + koff, db_lo + koff, idesc, 1u);
             }
             tc_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == P.b_stages) { stage = 0; phase ^= 1; }
+            if (++in_chain == CHUNK || it + 1 == k_iters) {
+              tc_commit(&tfull_bar[buf]);
+              if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+              in_chain = 0;
+            }
           }
-          tc_commit(&tfull_bar[buf]);
-          if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+          tc_commit(&aempty_bar[as]);
+          if (++as == A_STAGES) { as = 0; aphase ^= 1; }
         }
         JB_TRACE3(1, 2, seq);
       }
@@ -406,6 +438,7 @@ bool conv_gemm_tc3_eligible(const ConvGemmProblem& p) {
   if (e.post_scale != 1.0f) return false;
   if (p.n_pad > BIAS_BYTES / 4 || p.out_rows != p.m_rows) return false;
   if (p.rate > 1) return false;
+  if (p.tap_stride < 0 || (p.taps - 1) * p.tap_stride > A_SLAB_ROWS - BM) return false;
   if (e.act == ACT_GLU && (e.out_hi || e.res_f32)) return false;
   auto f32_ok = [&](const float* ptr, int ld) { return ptr == nullptr || (ld % 4 == 0 && ld >= p.n && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0); };
   auto h_ok = [&](const bf16* ptr, int ld) { return ptr == nullptr || (ld % 8 == 0 && ld >= p.n && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0); };
@@ -418,8 +451,9 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   const ConvGemmEpilogue& e = p.ep;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo;
   const int a_cols = p.a_cols > 0 ? p.a_cols : p.k_pad;
-  JB_PROPAGATE(make_tmap(&ta_hi, p.a_hi, p.a_rows, a_cols, p.a_ld, BM));
-  JB_PROPAGATE(make_tmap(&ta_lo, p.a_lo, p.a_rows, a_cols, p.a_ld, BM));
+  const int halo_rows = round_up(BM + (p.taps - 1) * p.tap_stride, 8);
+  JB_PROPAGATE(make_tmap(&ta_hi, p.a_hi, p.a_rows, a_cols, p.a_ld, halo_rows));
+  JB_PROPAGATE(make_tmap(&ta_lo, p.a_lo, p.a_rows, a_cols, p.a_ld, halo_rows));
   JB_PROPAGATE(make_tmap(&tb_hi, p.w_hi, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BN));
   JB_PROPAGATE(make_tmap(&tb_lo, p.w_lo, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BN));
   tres = tf32 = thi = tlo = ta_hi;
@@ -447,6 +481,10 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.has_f32 = e.out_f32 != nullptr;
   kp.has_split = e.out_hi != nullptr;
   kp.entry_bytes = ((kp.has_res || kp.has_f32) ? F32_SLAB_BYTES : 0) + (kp.has_split ? 2 * H16_SLAB_BYTES : 0);
+  kp.halo_rows = halo_rows;
+  // three weight stages when the epilogue ring still gets three entries, else two
+  kp.b_stages = (227 * 1024 - smem_fixed(3)) / kp.entry_bytes >= 3 ? 3 : 2;
+  const int SMEM_FIXED = smem_fixed(kp.b_stages);
   int entries = (227 * 1024 - SMEM_FIXED) / kp.entry_bytes;
   if (entries > MAX_ENTRIES) entries = MAX_ENTRIES;
   JB_REQUIRE(entries >= 2, -2, "conv_gemm_tc3: shared memory budget exceeded");
