@@ -472,18 +472,22 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
         uint8_t* bufA = ep_base + e * entry_bytes;
         uint8_t* bufB = bufA + (P.ep_bufs - 1) * C::SLAB_BYTES;   // == bufA when an entry is a single slab
-        const float* bs = bias_s + n0 + s * C::SLAB + half * CW;
+        const uint32_t bs_addr = smem_u32(bias_s) + static_cast<uint32_t>(n0 + s * C::SLAB + half * CW) * 4u;
 #pragma unroll
         for (int c = 0; c < CW / 8; ++c) {
           const uint32_t off = row_off + ((static_cast<uint32_t>(half * (CW / 8) + c) ^ sw) << 4);
           float v[8];
+          {
+            const uint4 b0 = lds128(bs_addr + c * 32), b1 = lds128(bs_addr + c * 32 + 16);   // 8 bias values, shared-space loads
+            const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x = __uint_as_float(r[c * 8 + i]) + bs[c * 8 + i];
-            v[i] = fmaxf(x, x * act_slope);   // LeakyReLU (slope in (0,1)); act_slope == 1 -> identity
+            for (int i = 0; i < 8; ++i) {
+              const float x = __uint_as_float(r[c * 8 + i]) + __uint_as_float(bv[i]);
+              v[i] = fmaxf(x, x * act_slope);   // LeakyReLU (slope in (0,1)); act_slope == 1 -> identity
+            }
           }
           if (P.has_res) {
-            const uint4 t = *reinterpret_cast<const uint4*>(bufA + off);
+            const uint4 t = lds128(smem_u32(bufA) + off);
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -496,7 +500,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             }
           }
           if (P.has_acc) {
-            const uint4 t = *reinterpret_cast<const uint4*>(bufB + off);
+            const uint4 t = lds128(smem_u32(bufB) + off);
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -510,7 +514,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(bufA + off) = o;
+            sts128(smem_u32(bufA) + off, o);
           }
           if (P.has_out1) {
             const float sl = P.out1_slope;
@@ -519,7 +523,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             o.y = pack_bf16x2(fmaxf(v[2], v[2] * sl), fmaxf(v[3], v[3] * sl));
             o.z = pack_bf16x2(fmaxf(v[4], v[4] * sl), fmaxf(v[5], v[5] * sl));
             o.w = pack_bf16x2(fmaxf(v[6], v[6] * sl), fmaxf(v[7], v[7] * sl));
-            *reinterpret_cast<uint4*>(bufB + off) = o;
+            sts128(smem_u32(bufB) + off, o);
           }
         }
         fence_proxy_async_smem();            // make the generic-proxy smem writes visible to the TMA engine

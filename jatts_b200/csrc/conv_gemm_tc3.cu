@@ -342,19 +342,33 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           mbar_wait(&epfull_bar[e], ph);
           uint8_t* ebuf = ep_base + e * P.entry_bytes;
           float v[32];
+          const uint32_t bias_addr = smem_u32(bias_s);
+          auto bias32 = [&](int col0, float (&b)[32]) {   // 32 consecutive bias values by shared-space 128-bit loads
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 t = lds128(bias_addr + static_cast<uint32_t>(col0 + 4 * q) * 4u);
+              b[4 * q] = __uint_as_float(t.x); b[4 * q + 1] = __uint_as_float(t.y);
+              b[4 * q + 2] = __uint_as_float(t.z); b[4 * q + 3] = __uint_as_float(t.w);
+            }
+          };
           if (P.act == ACT_GLU) {
             // tile columns [0,64) linear half, [64,128) gate half of the same 64 output channels
+            float ba[32], bg[32];
+            bias32(n0 + (s & 1) * 32, ba);
+            bias32(n0 + 64 + (s & 1) * 32, bg);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int ca = (s & 1) * 32 + i;   // s < 2 in GLU mode
-              const float a = accr[ca] + bias_s[n0 + ca];
-              const float g = accr[64 + ca] + bias_s[n0 + 64 + ca];
+              const float a = accr[ca] + ba[i];
+              const float g = accr[64 + ca] + bg[i];
               v[i] = a * (1.0f / (1.0f + __expf(-g))) * P.scale;
             }
           } else {
+            float bb[32];
+            bias32(n0 + s * 32, bb);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float x = accr[s * 32 + i] + bias_s[n0 + s * 32 + i];
+              float x = accr[s * 32 + i] + bb[i];
               if (P.act == ACT_RELU) x = fmaxf(x, 0.f);
               else if (P.act == ACT_TANH) x = tanhf(x);
               v[i] = x * P.scale;
@@ -366,12 +380,14 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
               const uint32_t off = f_row + ((static_cast<uint32_t>(c) ^ f_sw) << 4);
               float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
               if (P.has_res) {
-                const float4 r4 = *reinterpret_cast<const float4*>(ebuf + f32_off + off);
+                const uint4 ru = lds128(smem_u32(ebuf) + f32_off + off);
+                const float4 r4 = make_float4(__uint_as_float(ru.x), __uint_as_float(ru.y), __uint_as_float(ru.z), __uint_as_float(ru.w));
                 o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
                 v[4 * c] = o.x; v[4 * c + 1] = o.y; v[4 * c + 2] = o.z; v[4 * c + 3] = o.w;
               }
               if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (P.has_f32) *reinterpret_cast<float4*>(ebuf + f32_off + off) = o;
+              if (P.has_f32)
+                sts128(smem_u32(ebuf) + f32_off + off, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
             }
           }
           if (P.has_split) {
@@ -388,8 +404,8 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                 ph4[j] = *reinterpret_cast<uint32_t*>(&hh);
                 pl4[j] = *reinterpret_cast<uint32_t*>(&ll);
               }
-              *reinterpret_cast<uint4*>(ebuf + hi_off + off) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
-              *reinterpret_cast<uint4*>(ebuf + lo_off + off) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
+              sts128(smem_u32(ebuf) + hi_off + off, make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]));
+              sts128(smem_u32(ebuf) + lo_off + off, make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]));
             }
           }
           fence_proxy_async_smem();

@@ -169,7 +169,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   }
   // the t slabs' 16 tail rows are read by the shifted conv2 taps but never written: zero everything once
   for (int i = threadIdx.x; i < P.nt * K::T_BYTES / 16; i += kThreadsP)
-    reinterpret_cast<uint4*>(t_base)[i] = make_uint4(0u, 0u, 0u, 0u);
+    sts128(smem_u32(t_base) + static_cast<uint32_t>(i) * 16u, make_uint4(0u, 0u, 0u, 0u));
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -333,7 +333,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (lane_group == 0 && lane == 0) PT(2, 0, i);
       if (lane_group == 0 && lane == 0) PT(2, 1, i);
       tc_fence_after();
-      uint8_t* trow = t_base + tb * K::T_BYTES + row_off;
+      const uint32_t trow = smem_u32(t_base + tb * K::T_BYTES) + row_off;
 #pragma unroll
       for (int s = 0; s < C / 32; ++s) {
         uint32_t r[32];
@@ -356,7 +356,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           uint4 o;
           o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
           o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(trow + ((static_cast<uint32_t>(s * 4 + c) ^ sw) << 4)) = o;
+          sts128(trow + ((static_cast<uint32_t>(s * 4 + c) ^ sw) << 4), o);
         }
       }
       if (lane_group == 0 && lane == 0) PT(2, 4, i);
@@ -403,7 +403,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (P.leader_poll) named_bar_sync(3 + grp, 128);
       if (lane_group == 0 && lane == 0) PT(3, 0, i);
       tc_fence_after();
-      uint8_t* srow_p = slab_base + ra.idx * P.slab_bytes + row_off;
+      const uint32_t srow_p = smem_u32(slab_base + ra.idx * P.slab_bytes) + row_off;
 #pragma unroll
       for (int s = 0; s < C / 32; ++s) {
         uint32_t r[32];
@@ -418,8 +418,8 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (active) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint4* p = reinterpret_cast<uint4*>(srow_p + ((static_cast<uint32_t>(s * 4 + c) ^ sw) << 4));
-            const uint4 xr = *p;
+            const uint32_t p = srow_p + ((static_cast<uint32_t>(s * 4 + c) ^ sw) << 4);
+            const uint4 xr = lds128(p);
             const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
             float v[8];
 #pragma unroll
@@ -445,7 +445,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *p = o;
+            sts128(p, o);
           }
         }
       }
