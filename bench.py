@@ -125,6 +125,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic():
+    """DRAM bytes (read + write) of the dominant kernel family per step, from the committed ncu capture
+    (profiles/r01_traffic.json, written by tools_step_metrics.py); None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
+def workload_config(world: int, extra: dict) -> dict:
+    cfg = {"workload": "FastSpeech2 (JSUT tts1) + HiFi-GAN V1 hop 300, batch 64 x 50 phonemes (~300 frames each) per GPU, "
+                       "seeded random-init weights (duration recipe A)",
+           "batch_per_gpu": BATCH, "t_text": T_TEXT, "parallelism": f"utterance-sharded replicas x{world}"}
+    cfg.update(extra)
+    return cfg
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -180,8 +198,7 @@ def run_reference(args, rank: int, world: int):
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FastSpeech2 (JSUT tts1) + HiFi-GAN V1 hop 300, 50-phoneme utterances, seeded random-init weights",
-                   "batch": BATCH, "t_text": T_TEXT, "sample_utterances_per_step": n_utt},
+        "config": workload_config(world, {"sample_utterances_per_step": n_utt}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{n_utt} of the {BATCH} utterances per step, per-utterance loop as tts_decode.py, "
                                    f"oracle port of the reference arithmetic (fp32 torch CPU)"},
@@ -292,39 +309,42 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
+    traffic = measured_traffic()
     hg_flops = hifigan_flops_per_frame(cfg_hg) * frames
     conv_share = 1.0 - 2.0 * (cfg_hg["channels"] >> 4) * 7 * 300 / hifigan_flops_per_frame(cfg_hg)  # minus output_conv
     achieved = hg_flops * conv_share / (prof["ms_bf16"] * 1e-3) / 1e12
     fs2_fl = sum(fs2_flops(cfg_fs2, T_TEXT, int(o["feat_gen"].shape[0])) for o in outs)
     cpu_cores = os.cpu_count() or 1
     torch.set_num_threads(cpu_cores)
-    cpu_audio, cpu_times = time_cpu(1, reps=3, warm=1)
+    cpu_audio, cpu_times = time_cpu(4, reps=20, warm=1)   # ~10 s of CPU work
     cpu_value = cpu_audio * len(cpu_times) / sum(cpu_times)
     line = {
         "metric": METRIC, "value": total_audio * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "FastSpeech2 (JSUT tts1) + HiFi-GAN V1 hop 300, batch 64 x 50 phonemes (~300 frames each) per GPU, "
-                               "seeded random-init weights (duration recipe A)",
-                   "batch_per_gpu": BATCH, "t_text": T_TEXT, "mel_frames_per_gpu": frames,
+        "config": workload_config(world, {"mel_frames_per_gpu": frames,
                    "audio_seconds_per_step_per_gpu": audio_s, "sampling_rate": recipes.SAMPLING_RATE,
-                   "hop_size": recipes.HOP_SIZE, "parallelism": f"utterance-sharded replicas x{world}",
-                   "l2": "256 MB buffer written between timed steps; per-step activation working set ~3 GB >> 126 MB L2",
-                   "precision": "HiFi-GAN: bf16 operands / fp32 TMEM accumulate; FastSpeech2 GEMMs: fp16 hi+lo split (3 MMA) / fp32"},
+                   "hop_size": recipes.HOP_SIZE,
+                   "l2": "256 MB buffer written between timed steps; per-step activation working set ~2 GB >> 126 MB L2",
+                   "precision": "HiFi-GAN: bf16 operands / fp32 TMEM accumulate; FastSpeech2 GEMMs: fp16 hi+lo split (3 MMA) / fp32"}),
         "e2e": {"value": total_audio * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(tok_host.numel() * 8), "d2h_bytes_per_step": int(frames * recipes.HOP_SIZE * 4),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_bf16_tma_kernel<*> (all HiFi-GAN Conv1d/ConvTranspose1d launches of one step)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "HiFi-GAN convolution kernels: mrf_pair_kernel<C,k> (fused residual units, C = 32/64) + "
+                               "conv_bf16_tma_kernel<*> (all other Conv1d / ConvTranspose1d launches of one step)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src,
+                     "traffic": (traffic or {}).get("hifigan_conv_dram_bytes_per_step"),
+                     "traffic_source": (traffic or {}).get("source"),
                      "launches_per_step": int(prof["n_bf16"]), "kernel_ms_per_step": prof["ms_bf16"],
                      "algorithmic_flop_per_step": hg_flops * conv_share,
                      "fs2_split_gemm": {"launches_per_step": int(prof_fs2["n_split"]), "kernel_ms_per_step": prof_fs2["ms_split"],
                                         "algorithmic_flop_per_step": fs2_fl}},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "1 utterance (50 phonemes) x 3 repetitions after 1 warm-up, per-utterance loop as "
+                         "sample": "4 of the 64 utterances (50 phonemes each) x 20 repetitions after 1 warm-up, per-utterance loop as "
                                    "tts_decode.py; oracle port of the reference arithmetic, fp32 torch CPU"},
     }
     print(json.dumps(line), flush=True)
