@@ -121,6 +121,12 @@ JATTS_API void jatts_hifigan_destroy(jatts_hifigan* h);
 JATTS_API int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int32_t* h_mel_lens, int32_t n_utt,
                       float* d_wave, void* stream);
 
+/* Same generator with the output written as PCM_16 samples, int16 = lrintf(wave * 32767) -- what libsndfile stores
+ * when jatts/bin/tts_decode.py:250-255 calls sf.write(path, y, sr, "PCM_16"); the conversion is fused into the
+ * output convolution so the batched front-end (jatts_b200/decode.py) copies 2 bytes per sample to the host. */
+JATTS_API int jatts_hifigan_run_pcm16(jatts_hifigan* h, const float* d_mel, const int32_t* h_mel_lens, int32_t n_utt,
+                            int16_t* d_pcm, void* stream);
+
 /* ---- op-level entry points used by the parity tests (tests/test_ops_gpu.py) ------------------------ */
 typedef struct {
   const void* d_a_hi; const void* d_a_lo;     /* [a_rows, a_ld]; bf16 if a_lo NULL, else fp16 (hi, lo*2^11) pair */

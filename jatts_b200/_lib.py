@@ -71,7 +71,7 @@ class MrfPairArgs(C.Structure):
 EXPORTS = (
     "jatts_abi_version", "jatts_last_error", "jatts_launch_count",
     "jatts_fs2_create", "jatts_fs2_destroy", "jatts_fs2_plan", "jatts_fs2_run",
-    "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_op_conv_gemm", "jatts_op_mrf_pair",
+    "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_hifigan_run_pcm16", "jatts_op_conv_gemm", "jatts_op_mrf_pair",
     "jatts_profile_begin", "jatts_profile_end", "jatts_debug_set_trace",
 )
 
@@ -97,6 +97,8 @@ def _load():
     lib.jatts_hifigan_destroy.restype = None
     lib.jatts_hifigan_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
                                       C.c_void_p]
+    lib.jatts_hifigan_run_pcm16.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
+                                            C.c_void_p]
     lib.jatts_op_conv_gemm.argtypes = [C.POINTER(ConvGemmArgs), C.c_int32, C.c_void_p]
     lib.jatts_op_mrf_pair.argtypes = [C.POINTER(MrfPairArgs), C.c_void_p]
     lib.jatts_debug_set_trace.argtypes = [C.c_void_p]

@@ -189,9 +189,9 @@ extern "C" void jatts_hifigan_destroy(jatts_hifigan* h) {
   delete h;
 }
 
-extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int32_t* h_mel_lens, int32_t n_utt,
-                                 float* d_wave, void* stream) {
-  JB_REQUIRE(h && d_mel && h_mel_lens && d_wave && n_utt > 0, JATTS_E_INVALID, "hifigan_run: bad argument");
+static int hifigan_run_impl(jatts_hifigan* h, const float* d_mel, const int32_t* h_mel_lens, int32_t n_utt,
+                            float* d_wave, int16_t* d_pcm, void* stream) {
+  JB_REQUIRE(h && d_mel && h_mel_lens && (d_wave || d_pcm) && n_utt > 0, JATTS_E_INVALID, "hifigan_run: bad argument");
   JB_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const jatts_hifigan_config& c = h->cfg;
@@ -336,6 +336,19 @@ extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int
     cur = nxt;
     c_in = co;
   }
-  JB_PROPAGATE(output_conv_tanh(h->y[cur], c_in, c_in, h->out_w, h->out_b, c.kernel_size, L, h->hop, d_off, d_wave, s));
+  JB_PROPAGATE(output_conv_tanh(h->y[cur], c_in, c_in, h->out_w, h->out_b, c.kernel_size, L, h->hop, d_off, d_wave,
+                                reinterpret_cast<short*>(d_pcm), s));
   return 0;
+}
+
+extern "C" int jatts_hifigan_run(jatts_hifigan* h, const float* d_mel, const int32_t* h_mel_lens, int32_t n_utt,
+                                 float* d_wave, void* stream) {
+  JB_REQUIRE(d_wave != nullptr, JATTS_E_INVALID, "hifigan_run: null output");
+  return hifigan_run_impl(h, d_mel, h_mel_lens, n_utt, d_wave, nullptr, stream);
+}
+
+extern "C" int jatts_hifigan_run_pcm16(jatts_hifigan* h, const float* d_mel, const int32_t* h_mel_lens, int32_t n_utt,
+                                       int16_t* d_pcm, void* stream) {
+  JB_REQUIRE(d_pcm != nullptr, JATTS_E_INVALID, "hifigan_run_pcm16: null output");
+  return hifigan_run_impl(h, d_mel, h_mel_lens, n_utt, nullptr, d_pcm, stream);
 }

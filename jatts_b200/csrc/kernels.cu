@@ -1139,7 +1139,7 @@ static constexpr int OC_MAXK = 7;
 
 __global__ void output_conv_tanh_kernel(const bf16* __restrict__ x, int ld, int c, const float* __restrict__ w,
                                         float bias, int k, RowLayout L, int rate, const int* __restrict__ frame_off,
-                                        float* __restrict__ wave, long long total_rows) {
+                                        float* __restrict__ wave, short* __restrict__ pcm, long long total_rows) {
   extern __shared__ float ws[];  // [k][c]
   for (int i = threadIdx.x; i < k * c; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -1183,17 +1183,21 @@ __global__ void output_conv_tanh_kernel(const bf16* __restrict__ x, int ld, int 
     const int b = L.frame_seg[static_cast<int>(row / rate)];
     if (b < 0) continue;
     const long long t = row - static_cast<long long>(L.seg_start[b]) * rate;
-    wave[static_cast<long long>(frame_off[b]) * rate + t] = tanhf(acc[o]);
+    const float y = tanhf(acc[o]);
+    const long long idx = static_cast<long long>(frame_off[b]) * rate + t;
+    if (wave) wave[idx] = y;
+    // PCM_16 as libsndfile writes float data (sf.write(..., "PCM_16"), tts_decode.py:250-255): lrintf(y * 0x7FFF)
+    if (pcm) pcm[idx] = static_cast<short>(__float2int_rn(y * 32767.0f));
   }
 }
 int output_conv_tanh(const bf16* x, int ld, int c, const float* w, float bias, int k, RowLayout L, int rate,
-                     const int* frame_off, float* wave, cudaStream_t s) {
+                     const int* frame_off, float* wave, short* pcm, cudaStream_t s) {
   JB_REQUIRE(c % 8 == 0 && ld % 8 == 0 && k <= OC_MAXK, -2, "output_conv: C % 8, k <= 7");
   const long long total = static_cast<long long>(L.n_rows) * rate;
   if (total == 0) return 0;
   const long long threads = (total + OC_PER - 1) / OC_PER;
   output_conv_tanh_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, sizeof(float) * k * c, s>>>(
-      x, ld, c, w, bias, k, L, rate, frame_off, wave, total);
+      x, ld, c, w, bias, k, L, rate, frame_off, wave, pcm, total);
   JB_KERNEL_OK();
   return 0;
 }

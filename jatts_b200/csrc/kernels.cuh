@@ -63,8 +63,8 @@ int pack_mel_affine(const float* mel, int c, const float* a, const float* b, Row
                     int out_ld, cudaStream_t s);
 
 // HiFi-GAN output_conv: Conv1d(C -> 1, k) + tanh on an (already LeakyReLU'd) bf16 [rows*rate, ld] matrix.
-// wave: fp32, utterance-contiguous [sum T*rate]
+// wave: fp32, utterance-contiguous [sum T*rate] and / or pcm: int16 = lrintf(wave * 32767) (either may be null)
 int output_conv_tanh(const bf16* x, int ld, int c, const float* w /*[k][c]*/, float bias, int k, RowLayout L,
-                     int rate, const int* frame_off, float* wave, cudaStream_t s);
+                     int rate, const int* frame_off, float* wave, short* pcm, cudaStream_t s);
 
 }  // namespace jb

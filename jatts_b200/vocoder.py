@@ -193,8 +193,10 @@ class HiFiGANGenerator(torch.nn.Module):
         raise NotImplementedError("inference only: use inference() / inference_batch()")
 
     @torch.no_grad()
-    def inference_batch(self, mels: Sequence[torch.Tensor], normalize_before: bool = False) -> List[torch.Tensor]:
-        """list of (T_i, in_channels) -> list of (T_i*hop, 1) fp32 waveforms."""
+    def inference_batch(self, mels: Sequence[torch.Tensor], normalize_before: bool = False,
+                        pcm16: bool = False) -> List[torch.Tensor]:
+        """list of (T_i, in_channels) -> list of (T_i*hop, 1) fp32 waveforms, or int16 PCM samples
+        (``lrintf(wave * 32767)``, what ``sf.write(..., "PCM_16")`` stores) when ``pcm16`` is set."""
         if len(mels) == 0:
             return []
         handle = self._get_engine(normalize_before)
@@ -206,12 +208,12 @@ class HiFiGANGenerator(torch.nn.Module):
             if m.dim() != 2 or m.shape[1] != self._cfg["in_channels"]:
                 raise ValueError(f"expected (T, {self._cfg['in_channels']}) mel, got {tuple(m.shape)}")
         cat = torch.cat([m.to(device=dev, dtype=torch.float32) for m in mels], 0).contiguous()
-        wave = torch.empty(sum(lens) * self.hop, device=dev, dtype=torch.float32)
+        wave = torch.empty(sum(lens) * self.hop, device=dev, dtype=torch.int16 if pcm16 else torch.float32)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             h_lens = (C.c_int32 * len(lens))(*lens)
-            _lib.check(_lib.lib.jatts_hifigan_run(handle, cat.data_ptr(), h_lens, len(lens), wave.data_ptr(), stream),
-                       "hifigan_run")
+            run = _lib.lib.jatts_hifigan_run_pcm16 if pcm16 else _lib.lib.jatts_hifigan_run
+            _lib.check(run(handle, cat.data_ptr(), h_lens, len(lens), wave.data_ptr(), stream), "hifigan_run")
         outs, o = [], 0
         for n in lens:
             outs.append(wave[o:o + n * self.hop].unsqueeze(-1))
@@ -288,8 +290,10 @@ class Vocoder(object):
         self.model = self.model.eval().to(device)
 
     @torch.no_grad()
-    def decode_batch(self, cs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-        return [y.view(-1) for y in self.model.inference_batch(list(cs), normalize_before=False)]
+    def decode_batch(self, cs: Sequence[torch.Tensor], pcm16: bool = False) -> List[torch.Tensor]:
+        """batched ``decode``: list of (T_i, 80) normalised mels -> list of (T_i*hop,) waveforms (fp32, or the
+        int16 PCM_16 samples tts_decode.py writes when ``pcm16``)."""
+        return [y.view(-1) for y in self.model.inference_batch(list(cs), normalize_before=False, pcm16=pcm16)]
 
     @torch.no_grad()
     def decode(self, c):

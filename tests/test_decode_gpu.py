@@ -1,0 +1,85 @@
+"""GPU tests of the batched stage-4 front-end (jatts_b200/decode.py): fused PCM_16 output and the command-line
+path with the recipe's file formats (csv, tokens.txt, config.yml, checkpoint .pkl, stats), checked against the
+per-utterance reference-shaped calls ``model.inference`` -> ``vocoder.decode`` -> PCM_16 rounding."""
+import wave
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+import jatts_b200
+from jatts_b200 import decode
+from oracle import recipes
+
+
+def pcm16_of(y: torch.Tensor) -> torch.Tensor:
+    """what libsndfile stores for float data written as PCM_16: lrintf(y * 0x7FFF) (round half to even)"""
+    return torch.round(y.float() * 32767.0).to(torch.int16)
+
+
+@pytest.mark.gpu
+def test_pcm16_is_the_rounded_float_waveform():
+    cfg = recipes.HIFIGAN_TINY
+    g = jatts_b200.HiFiGANGenerator(**cfg)
+    g.load_state_dict(recipes.make_hifigan_state_dict(cfg, 0))
+    g = g.eval().to("cuda")
+    mels = [recipes.make_mel(t, i) for i, t in enumerate([33, 1, 80])]
+    ys = g.inference_batch(mels)
+    ps = g.inference_batch(mels, pcm16=True)
+    for y, p in zip(ys, ps):
+        assert p.dtype == torch.int16 and p.shape == y.shape
+        assert torch.equal(p.cpu(), pcm16_of(y.cpu()))          # bit exact: same kernel, same accumulator
+
+
+@pytest.mark.gpu
+def test_cli_writes_the_per_utterance_samples(tmp_path):
+    cfg, hcfg = recipes.JSUT_FS2, recipes.HIFIGAN_TINY
+    sd = recipes.make_fs2_state_dict(cfg, seed=0, duration_recipe="A")
+    hsd = recipes.make_hifigan_state_dict(hcfg, seed=0)
+    tstats, vstats = recipes.make_stats(1), recipes.make_stats(2)
+    # ---- the recipe's files
+    vocab = ["<blank>", "<unk>"] + [f"p{i}" for i in range(2, cfg["idim"] - 1)] + ["<sos/eos>"]
+    (tmp_path / "tokens.txt").write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    lens = [9, 31, 4, 17, 9, 50, 1]
+    rows = ["sample_id,phonemes"]
+    texts = []
+    for i, n in enumerate(lens):
+        ids = recipes.make_phonemes(n, 300 + i, cfg["idim"]).tolist()
+        toks = [vocab[t] for t in ids]
+        if i == 3:
+            toks[2] = "not-in-vocab"        # -> <unk> (id 1)
+            ids[2] = 1
+        texts.append(torch.tensor(ids, dtype=torch.long))
+        rows.append(f"utt{i}," + " ".join(toks))
+    (tmp_path / "dev.csv").write_text("\n".join(rows) + "\n", encoding="utf-8")
+    np.savez(tmp_path / "stats.npz", mel_mean=tstats["mean"].numpy(), mel_scale=tstats["scale"].numpy())
+    np.savez(tmp_path / "voc_stats.npz", mean=vstats["mean"].numpy(), scale=vstats["scale"].numpy())
+    torch.save({"model": {"generator": hsd}}, tmp_path / "voc.pkl")
+    with open(tmp_path / "voc_config.yml", "w") as f:
+        yaml.safe_dump({"generator_type": "HiFiGANGenerator", "sampling_rate": 24000,
+                        "generator_params": {k: (list(map(list, v)) if k == "resblock_dilations" else list(v) if isinstance(v, tuple) else v)
+                                             for k, v in hcfg.items()}}, f)
+    torch.save({"model": sd}, tmp_path / "checkpoint-1steps.pkl")
+    with open(tmp_path / "config.yml", "w") as f:
+        yaml.safe_dump({"model_type": "FastSpeech2", "model_params": dict(cfg), "out_feat_type": "mel", "feat_list": ["mel"],
+                        "sampling_rate": 24000,
+                        "vocoder": {"checkpoint": str(tmp_path / "voc.pkl"), "config": str(tmp_path / "voc_config.yml"),
+                                    "stats": str(tmp_path / "voc_stats.npz")}}, f)
+    out = tmp_path / "out"
+    rc = decode.main(["--csv", str(tmp_path / "dev.csv"), "--stats", str(tmp_path / "stats.npz"),
+                      "--token-list", str(tmp_path / "tokens.txt"), "--token-column", "phonemes", "--outdir", str(out),
+                      "--checkpoint", str(tmp_path / "checkpoint-1steps.pkl"), "--max-utts", "3", "--verbose", "0"])
+    assert rc == 0
+    # ---- the same utterances one at a time through the reference-shaped calls
+    model = jatts_b200.FastSpeech2(**cfg)
+    model.load_state_dict(sd)
+    model = model.eval().to("cuda")
+    voc = jatts_b200.Vocoder(hsd, {"generator_type": "HiFiGANGenerator", "generator_params": dict(hcfg), "sampling_rate": 24000},
+                             vstats, "cuda", trg_stats=tstats)
+    for i, x in enumerate(texts):
+        y, sr = voc.decode(model.inference(x.to("cuda"))["feat_gen"])
+        with wave.open(str(out / "wav" / f"utt{i}.wav"), "rb") as w:
+            assert w.getframerate() == sr == 24000 and w.getnchannels() == 1 and w.getsampwidth() == 2
+            got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+        assert np.array_equal(got, pcm16_of(y.cpu()).numpy()), f"utt{i}: wav samples differ from the per-utterance path"
