@@ -37,6 +37,8 @@ struct KernelParams2 {
   int m_rows;
   int num_m_tiles, num_n_tiles;
   int cl;           // CTAs per cluster sharing the streamed weight tiles by TMA multicast (HALO mode), else 1
+  int pair;         // 1: the cluster is a CTA pair issuing M = 256 cta_group::2 MMAs (cl == 2, HALO): each CTA keeps its own
+                    // 128 activation rows and HALF of every weight tile in shared memory
   int num_groups;   // ceil(num_m_tiles / cl) * num_n_tiles: a cluster walks groups of cl M tiles x one N tile
   const uint8_t* frame_mask;
   int rate;
@@ -129,7 +131,9 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <int BLOCK_N, int KCH, int MODE>
+// PAIR is a template parameter, not a runtime flag: a kernel that contains cta_group::2 instructions can only be
+// launched with an even cluster size ("cluster misconfiguration" otherwise, even if the path is never taken)
+template <int BLOCK_N, int KCH, int MODE, bool PAIR>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_bm,
@@ -139,6 +143,11 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   using C = Cfg2<BLOCK_N, KCH, MODE>;
   constexpr int STAGES = C::STAGES;
   constexpr int KSTEPS = KCH / UMMA_K2;
+  // weight ring: a CTA of a pair keeps half of each tile, so the same bytes give twice the depth (Little's law:
+  // bytes in flight = consumption rate x L2 latency; measured 55-60 % of the MMA rate with 4 x 16 KB per CTA)
+  constexpr int B_STAGE_BYTES = PAIR ? C::B_BYTES / 2 : C::B_BYTES;
+  constexpr int B_DEPTH = PAIR ? 2 * C::B_STAGES : C::B_STAGES;
+  static_assert(B_DEPTH <= 8, "barrier arrays");
   const int E = P.ep_entries;
   const int entry_bytes = P.ep_bufs * C::SLAB_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -181,7 +190,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (P.has_out1) tma_prefetch_desc(&tm_out1);
     for (int i = 0; i < NB; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], MODE == MODE_HALO ? cl : 1);   // multicast weight stage: freed by every CTA of the cluster
+      mbar_init(&empty_bar[i], (MODE == MODE_HALO && !PAIR) ? cl : 1);   // multicast weight stage: freed by every CTA of the cluster
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&afull_bar[i], 1);
@@ -189,7 +198,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], PAIR ? 8 : 4);   // pair: the leader's barrier also collects the peer's epilogue warps
     }
     for (int i = 0; i < ME; ++i) {
       mbar_init(&epfull_bar[i], 1);
@@ -200,10 +209,17 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = threadIdx.x; i < P.n_pad && i < C::BIAS_BYTES / 4; i += kThreads2) bias_s[i] = P.bias ? P.bias[i] : 0.f;
   tc_fence_before();
@@ -223,7 +239,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             tma_load_2d(&tm_b, wfull_bar, w_base + (kc * P.taps + tap) * C::B_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride);
       }
       const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * C::KROWB;
-      Ring rs(0, STAGES), ra(0, C::A_STAGES), rb(0, C::B_STAGES);
+      Ring rs(0, STAGES), ra(0, C::A_STAGES), rb(0, B_DEPTH);
       for (int grp = cid, seq = 0; grp < P.num_groups; grp += ncl, ++seq) {
         const int m0 = ((grp / P.num_n_tiles) * cl + rank) * BLOCK_M2;
         const int n0 = (grp % P.num_n_tiles) * BLOCK_N;
@@ -244,19 +260,34 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           for (int kc = 0; kc < P.k_chunks; ++kc) {
             mbar_wait(&aempty_bar[ra.idx], ra.phase ^ 1);
             if (kc == 0) JB_TRACE(0, 0, seq);
-            mbar_expect_tx(&afull_bar[ra.idx], a_bytes);
-            tma_load_2d(&tm_a, &afull_bar[ra.idx], smem + ra.idx * C::A_SLAB_BYTES, kc * KCH, m0 + P.tap_off0);
+            if constexpr (!PAIR) {
+              mbar_expect_tx(&afull_bar[ra.idx], a_bytes);
+              tma_load_2d(&tm_a, &afull_bar[ra.idx], smem + ra.idx * C::A_SLAB_BYTES, kc * KCH, m0 + P.tap_off0);
+            } else {
+              // both CTAs' slabs complete on the LEADER's barrier (only the leader's MMA thread waits on it)
+              if (rank == 0) mbar_expect_tx(&afull_bar[ra.idx], 2 * a_bytes);
+              tma_load_2d_pair(&tm_a, mapa_u32(smem_u32(&afull_bar[ra.idx]), 0), smem + ra.idx * C::A_SLAB_BYTES, kc * KCH,
+                               m0 + P.tap_off0);
+            }
             ra.next();
             if (MODE == MODE_HALO) {
               for (int tap = 0; tap < P.taps; ++tap) {
                 mbar_wait(&empty_bar[rb.idx], rb.phase ^ 1);
+                if constexpr (PAIR) {
+                  // this CTA's half of the weight tile (rows rank * N/2 ...) stays in its own shared memory
+                  if (rank == 0) mbar_expect_tx(&full_bar[rb.idx], C::B_BYTES);
+                  tma_load_2d_pair(&tm_bm, mapa_u32(smem_u32(&full_bar[rb.idx]), 0), b_base + rb.idx * B_STAGE_BYTES, kc * KCH,
+                                   P.w_row0 + tap * P.w_tap_stride + n0 + rank * (BLOCK_N / 2));
+                  rb.next();
+                  continue;
+                }
                 mbar_expect_tx(&full_bar[rb.idx], C::B_BYTES);
                 if (cl == 1) {
-                  tma_load_2d(&tm_b, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride + n0);
+                  tma_load_2d(&tm_b, &full_bar[rb.idx], b_base + rb.idx * B_STAGE_BYTES, kc * KCH, P.w_row0 + tap * P.w_tap_stride + n0);
                 } else {
                   // this CTA fetches rows [rank, rank + 1) * BLOCK_N / cl of the weight tile for the whole cluster
                   const int slice = BLOCK_N / cl;
-                  tma_load_2d_mc(&tm_bm, &full_bar[rb.idx], b_base + rb.idx * C::B_BYTES + rank * slice * C::KROWB, kc * KCH,
+                  tma_load_2d_mc(&tm_bm, &full_bar[rb.idx], b_base + rb.idx * B_STAGE_BYTES + rank * slice * C::KROWB, kc * KCH,
                                  P.w_row0 + tap * P.w_tap_stride + n0 + rank * slice, cl_mask);
                 }
                 rb.next();
@@ -272,10 +303,13 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     // issue one tcgen05.mma that executes in 16-32 clk, plus several hundred clk of mbarrier handling per
     // tile.  A second issuing warp made it worse (84 clk per MMA: the issue port is shared).  Tiles alternate
     // between the two TMEM accumulators / epilogue groups.
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
+    if ((!PAIR || rank == 0) && elect_one()) {
+      constexpr uint32_t idesc1 = make_idesc(BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
+      constexpr uint32_t idesc2 = make_idesc(2 * BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
+      constexpr uint32_t idesc = PAIR ? idesc2 : idesc1;
+      constexpr bool pair = PAIR;
       const int pipe = 0;
-      Ring rs(0, STAGES), ra(0, C::A_STAGES), rb(0, C::B_STAGES);
+      Ring rs(0, STAGES), ra(0, C::A_STAGES), rb(0, B_DEPTH);
       const uint32_t w_addr = smem_u32(w_base);
       // descriptor words: lo = (addr >> 4) | LBO(1) << 16 ; hi = SBO (8 rows) | version 1 | swizzle mode
       constexpr uint32_t desc_lo0 = 1u << 16;
@@ -325,7 +359,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                 mbar_wait(&full_bar[bs], rb.phase);
                 rb.next();
                 tc_fence_after();
-                b_addr = smem_u32(b_base + bs * C::B_BYTES);
+                b_addr = smem_u32(b_base + bs * B_STAGE_BYTES);
               } else {
                 b_addr = w_addr + static_cast<uint32_t>(kc * P.taps + tap) * C::B_BYTES;
               }
@@ -335,17 +369,24 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
               const uint32_t a_lo = desc_lo0 + ((slab + static_cast<uint32_t>(tap * P.tap_stride) * C::KROWB) >> 4);
               const uint32_t b_lo = desc_lo0 + (b_addr >> 4);
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                tc_mma_bf16_lohi(tmem_d, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < KSTEPS; ++k) {
+                if constexpr (MODE == MODE_HALO && PAIR)
+                  tc_mma_bf16_lohi_pair(tmem_d, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                else
+                  tc_mma_bf16_lohi(tmem_d, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              }
               if (MODE == MODE_HALO) {
-                if (cl == 1) tc_commit(&empty_bar[bs]);
+                if constexpr (PAIR) tc_commit_pair(&empty_bar[bs]);
+                else if (cl == 1) tc_commit(&empty_bar[bs]);
                 else tc_commit_mc(&empty_bar[bs], cl_mask);
               }
             }
-            tc_commit(&aempty_bar[as]);
+            if constexpr (MODE == MODE_HALO && PAIR) tc_commit_pair(&aempty_bar[as]);
+            else tc_commit(&aempty_bar[as]);
           }
         }
-        tc_commit(&tfull_bar[acc]);
+        if constexpr (MODE == MODE_HALO && PAIR) tc_commit_pair(&tfull_bar[acc]);
+        else tc_commit(&tfull_bar[acc]);
         if (pipe == 0) JB_TRACE(1, 2, seq);
       }
     }
@@ -468,7 +509,10 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           // every TMEM read of this accumulator has completed: hand it back to the MMA warp right away
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // the leader's MMA thread waits
+            else mbar_arrive(&tempty_bar[acc]);
+          }
         }
         uint8_t* bufA = ep_base + e * entry_bytes;
         uint8_t* bufB = bufA + (P.ep_bufs - 1) * C::SLAB_BYTES;   // == bufA when an entry is a single slab
@@ -538,9 +582,14 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   if (cl > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                   : "memory");
   }
 }
 
@@ -567,7 +616,7 @@ bool conv_gemm_tc2_eligible(const ConvGemmProblem& p) {
 }
 
 
-template <int BLOCK_N, int KCH, int MODE>
+template <int BLOCK_N, int KCH, int MODE, bool PAIR = false>
 static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   using C = Cfg2<BLOCK_N, KCH, MODE>;
   const ConvGemmEpilogue& e = p.ep;
@@ -582,8 +631,12 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   // C = 128 / 256 stages): CTAs of a cluster work on neighbouring M tiles in lockstep and share each weight tile
   // through TMA multicast, every CTA fetching 1/cl of it.
   static const int env_cl = getenv("JATTS_B200_TC2_CL") ? atoi(getenv("JATTS_B200_TC2_CL")) : 1;
+  // CTA pairs (cta_group::2, M = 256): each SM reads and is sent half of every weight tile, which takes the
+  // N = 128 convolutions off the shared-memory port ceiling
   int cl = 1;
-  if (MODE == MODE_HALO && (env_cl == 2 || env_cl == 4) && ceil_div(p.m_rows, BLOCK_M2) >= 2 * env_cl) cl = env_cl;
+  const int pair = PAIR ? 1 : 0;
+  if (PAIR) cl = 2;
+  else if (MODE == MODE_HALO && (env_cl == 2 || env_cl == 4) && ceil_div(p.m_rows, BLOCK_M2) >= 2 * env_cl) cl = env_cl;
   tbm = tb;
   if (cl > 1) JB_PROPAGATE(make_tmap(&tbm, p.w_hi, w_rows, p.k_pad, p.k_pad, BLOCK_N / cl, KCH));
   tres = tacc = to0 = to1 = ta;
@@ -603,6 +656,7 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.num_m_tiles = ceil_div(p.m_rows, BLOCK_M2);
   kp.num_n_tiles = (p.w_tap_stride != 0 ? p.n : p.n_pad) / BLOCK_N;
   kp.cl = cl;
+  kp.pair = pair;
   kp.num_groups = ceil_div(kp.num_m_tiles, cl) * kp.num_n_tiles;
   kp.frame_mask = p.frame_mask;
   kp.rate = p.rate > 0 ? p.rate : 1;
@@ -638,7 +692,7 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   static const char* sd_env = getenv("JATTS_B200_STORE_DEPTH");
   if (sd_env) kp.store_depth = atoi(sd_env) < entries - 1 ? atoi(sd_env) : entries - 2;
   const int smem_bytes = C::SMEM_FIXED + w_bytes + entries * entry;
-  auto kern = conv_bf16_tma_kernel<BLOCK_N, KCH, MODE>;
+  auto kern = conv_bf16_tma_kernel<BLOCK_N, KCH, MODE, PAIR>;
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
     JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -703,6 +757,10 @@ int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream) {
     return halo_ok && max_mode >= MODE_RESIDENT && (p.w_tap_stride != 0 ? p.n : p.n_pad) == p.block_n &&
            fixed + round_up(p.taps * ceil_div(a_cols, kch) * b_bytes, 1024) + 4 * 2 * 8192 <= 227 * 1024;
   };
+  // CTA pairs (cta_group::2, M = 256): each SM reads and is sent half of every weight tile, which takes the
+  // N >= 128 convolutions off the shared-memory port ceiling
+  static const int env_pair = getenv("JATTS_B200_TC2_PAIR") ? atoi(getenv("JATTS_B200_TC2_PAIR")) : 1;
+  const bool pair_ok = env_pair != 0 && ceil_div(p.m_rows, BLOCK_M2) >= 4;
   switch (p.block_n) {
     case 32:
       if (a_cols <= 32 && resident_ok(Cfg2<32, 32, MODE_RESIDENT>::SMEM_FIXED, Cfg2<32, 32, MODE_RESIDENT>::B_BYTES, 32))
@@ -717,8 +775,10 @@ int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream) {
     case 128:
       if (resident_ok(Cfg2<128, 64, MODE_RESIDENT>::SMEM_FIXED, Cfg2<128, 64, MODE_RESIDENT>::B_BYTES, 64))
         return launch2<128, 64, MODE_RESIDENT>(p, stream);
+      if (halo_ok && pair_ok) return launch2<128, 64, MODE_HALO, true>(p, stream);
       return halo_ok ? launch2<128, 64, MODE_HALO>(p, stream) : launch2<128, 64, MODE_STREAM>(p, stream);
     case 256:
+      if (halo_ok && pair_ok) return launch2<256, 64, MODE_HALO, true>(p, stream);
       return halo_ok ? launch2<256, 64, MODE_HALO>(p, stream) : launch2<256, 64, MODE_STREAM>(p, stream);
   }
   return -2;
