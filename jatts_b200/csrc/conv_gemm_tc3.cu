@@ -40,7 +40,7 @@ constexpr int UK = 16;
 constexpr int kThreads3 = 256;
 constexpr int CHUNK = 8;      // K blocks per accumulation chain
 constexpr int A_STAGES = 2;
-constexpr int MAX_B_STAGES = 3;
+constexpr int MAX_B_STAGES = 6;                // 3 full stages, or 6 half stages when a CTA pair shares the weights
 constexpr int OP_BYTES = BM * BK * 2;          // 16 KB: one weight tile (hi or lo)
 constexpr int B_STAGE_BYTES = 2 * OP_BYTES;    // B_hi | B_lo
 constexpr int A_SLAB_ROWS = 144;               // 128 + halo of the taps (<= 16 rows)
@@ -69,6 +69,7 @@ struct Params3 {
   int has_res, has_f32, has_split;
   int entries, entry_bytes;
   int b_stages;     // weight ring depth (2..3)
+  int num_groups;   // pair mode: ceil(num_m_tiles / 2) * num_n_tiles (a pair walks 2 M tiles x one N tile at a time)
   int halo_rows;    // rows of the activation slab: 128 + (taps-1)*tap_stride rounded up to 8
   long long* trace;
 };
@@ -99,6 +100,9 @@ __device__ __forceinline__ int tile_slabs(const Params3& P, int n0) {
   return left >= BN ? 4 : (left <= 0 ? 0 : (left + SLAB - 1) / SLAB);
 }
 
+// PAIR: the two CTAs of a cluster issue M = 256 cta_group::2 MMAs; each keeps its own 128 activation rows and HALF of
+// every weight tile pair (a template parameter: kernels with cta_group::2 code need an even cluster size to launch)
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads3, 1)
 gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -124,7 +128,16 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = P.num_m_tiles * P.num_n_tiles;
+  // tile schedule: work unit u -> (M tile, N tile).  Single CTA: u = tile index.  Pair: u = group index, CTA `rank`
+  // owns M tile 2 * (u / num_n_tiles) + rank (past the end: loads zero-fill, stores clip, rows are masked)
+  constexpr int CL = PAIR ? 2 : 1;
+  const int rank = PAIR ? static_cast<int>(blockIdx.x) & 1 : 0;
+  const int u0 = static_cast<int>(blockIdx.x) / CL;
+  const int ustep = static_cast<int>(gridDim.x) / CL;
+  const int num_units = PAIR ? P.num_groups : P.num_m_tiles * P.num_n_tiles;
+  constexpr int B_OP = PAIR ? OP_BYTES / 2 : OP_BYTES;          // one weight tile (hi or lo) as this CTA stores it
+  constexpr int B_STG = 2 * B_OP;                                // B_hi | B_lo
+  const int b_depth = PAIR ? 2 * P.b_stages : P.b_stages;
   const int k_iters = P.taps * P.k_chunks;
   const int n_chains = (k_iters + CHUNK - 1) / CHUNK;
   const int E = P.entries;
@@ -137,7 +150,7 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
     for (int i = 0; i < MAX_B_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], PAIR ? 8 : 4); }
     for (int i = 0; i < MAX_ENTRIES; ++i) {
       mbar_init(&epfull_bar[i], 1);
       mbar_init(&epempty_bar[i], 1);
@@ -146,10 +159,17 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(static_cast<uint32_t>(TMEM_COLS))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(static_cast<uint32_t>(TMEM_COLS))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(static_cast<uint32_t>(TMEM_COLS))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   {
     const int n_bias = P.act == ACT_GLU ? 2 * P.n : P.n;   // entries the bias tensor really has
@@ -158,6 +178,7 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's mbarriers exist before any remote arrive / pair load
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -167,37 +188,61 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       const uint32_t a_bytes = static_cast<uint32_t>(P.halo_rows) * BK * 2;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / P.num_n_tiles) * BM;
-        const int n0 = (tile % P.num_n_tiles) * BN;
+      for (int u = u0; u < num_units; u += ustep) {
+        const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
+        const int n0 = (u % P.num_n_tiles) * BN;
         for (int kc = 0; kc < P.k_chunks; ++kc) {
           mbar_wait(&aempty_bar[as], aphase ^ 1);
           uint8_t* a = smem + as * A_STAGE_BYTES;
-          mbar_expect_tx(&afull_bar[as], 2 * a_bytes);
-          tma_load_2d(&tm_a_hi, &afull_bar[as], a, kc * BK, m0 + P.tap_off0);
-          tma_load_2d(&tm_a_lo, &afull_bar[as], a + A_OP_BYTES, kc * BK, m0 + P.tap_off0);
+          if constexpr (PAIR) {
+            // both CTAs' slabs complete on the LEADER's barrier (only its MMA thread waits on it)
+            const uint32_t lb = mapa_u32(smem_u32(&afull_bar[as]), 0);
+            if (rank == 0) mbar_expect_tx(&afull_bar[as], 4 * a_bytes);
+            tma_load_2d_pair(&tm_a_hi, lb, a, kc * BK, m0 + P.tap_off0);
+            tma_load_2d_pair(&tm_a_lo, lb, a + A_OP_BYTES, kc * BK, m0 + P.tap_off0);
+          } else {
+            mbar_expect_tx(&afull_bar[as], 2 * a_bytes);
+            tma_load_2d(&tm_a_hi, &afull_bar[as], a, kc * BK, m0 + P.tap_off0);
+            tma_load_2d(&tm_a_lo, &afull_bar[as], a + A_OP_BYTES, kc * BK, m0 + P.tap_off0);
+          }
           if (++as == A_STAGES) { as = 0; aphase ^= 1; }
           for (int tap = 0; tap < P.taps; ++tap) {
             const int brow = tap * P.n_pad + n0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* b = b_ring + stage * B_STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], B_STAGE_BYTES);
-            tma_load_2d(&tm_b_hi, &full_bar[stage], b, kc * BK, brow);
-            tma_load_2d(&tm_b_lo, &full_bar[stage], b + OP_BYTES, kc * BK, brow);
-            if (++stage == P.b_stages) { stage = 0; phase ^= 1; }
+            uint8_t* b = b_ring + stage * B_STG;
+            if constexpr (PAIR) {
+              // this CTA's half (rows rank * 64 ...) of the hi and lo weight tiles stays in its own shared memory
+              const uint32_t lb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], B_STAGE_BYTES);
+              tma_load_2d_pair(&tm_b_hi, lb, b, kc * BK, brow + rank * (BN / 2));
+              tma_load_2d_pair(&tm_b_lo, lb, b + B_OP, kc * BK, brow + rank * (BN / 2));
+            } else {
+              mbar_expect_tx(&full_bar[stage], B_STAGE_BYTES);
+              tma_load_2d(&tm_b_hi, &full_bar[stage], b, kc * BK, brow);
+              tma_load_2d(&tm_b_lo, &full_bar[stage], b + B_OP, kc * BK, brow);
+            }
+            if (++stage == b_depth) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, /*is_bf16=*/false);   // fp16 operands
+    if ((!PAIR || rank == 0) && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, BN, /*is_bf16=*/false);   // fp16 operands
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if constexpr (PAIR) tc_mma_f16_pair(d, da, db, idesc, acc);
+        else tc_mma_bf16(d, da, db, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) tc_commit_pair(bar);
+        else tc_commit(bar);
+      };
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       int buf = 0;
       uint32_t buf_phase = 0;
-      for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
+      for (int u = u0, seq = 0; u < num_units; u += ustep, ++seq) {
         JB_TRACE3(1, 0, seq);
         int it = 0;          // (K chunk, tap) steps issued for this tile
         int in_chain = 0;    // steps accumulated into the current chain
@@ -215,28 +260,28 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
             }
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sb = smem_u32(b_ring + stage * B_STAGE_BYTES);
+            const uint32_t sb = smem_u32(b_ring + stage * B_STG);
             // tap t reads activation rows [t*stride, t*stride + 128) of the slab (row-shifted descriptor start)
             const uint32_t a_tap = sa + static_cast<uint32_t>(tap * P.tap_stride) * (BK * 2);
             const uint64_t da_hi = desc128(a_tap), db_hi = desc128(sb);
-            const uint64_t da_lo = desc128(a_tap + A_OP_BYTES), db_lo = desc128(sb + OP_BYTES);
+            const uint64_t da_lo = desc128(a_tap + A_OP_BYTES), db_lo = desc128(sb + B_OP);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
               const uint64_t koff = static_cast<uint64_t>((k * UK * 2) >> 4);
               const uint32_t first = (in_chain != 0 || k != 0) ? 1u : 0u;
-              tc_mma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, first);
-              tc_mma_bf16(tmem_c, da_lo + koff, db_hi + koff, idesc, first);
-              tc_mma_bf16(tmem_c, da_hi + koff, db_lo + koff, idesc, 1u);
+              mma(tmem_d, da_hi + koff, db_hi + koff, first);
+              mma(tmem_c, da_lo + koff, db_hi + koff, first);
+              mma(tmem_c, da_hi + koff, db_lo + koff, 1u);
             }
-            tc_commit(&empty_bar[stage]);
-            if (++stage == P.b_stages) { stage = 0; phase ^= 1; }
+            commit(&empty_bar[stage]);
+            if (++stage == b_depth) { stage = 0; phase ^= 1; }
             if (++in_chain == CHUNK || it + 1 == k_iters) {
-              tc_commit(&tfull_bar[buf]);
+              commit(&tfull_bar[buf]);
               if (++buf == 2) { buf = 0; buf_phase ^= 1; }
               in_chain = 0;
             }
           }
-          tc_commit(&aempty_bar[as]);
+          commit(&aempty_bar[as]);
           if (++as == A_STAGES) { as = 0; aphase ^= 1; }
         }
         JB_TRACE3(1, 2, seq);
@@ -247,9 +292,9 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     if (elect_one()) {
       int e = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / P.num_n_tiles) * BM;
-        const int n0 = (tile % P.num_n_tiles) * BN;
+      for (int u = u0; u < num_units; u += ustep) {
+        const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
+        const int n0 = (u % P.num_n_tiles) * BN;
         const int ns = tile_slabs(P, n0);
         const int o0 = P.act == ACT_GLU ? n0 / 2 : n0;
         for (int s = 0; s < ns; ++s) {
@@ -269,9 +314,9 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     if (elect_one()) {
       int e = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / P.num_n_tiles) * BM;
-        const int n0 = (tile % P.num_n_tiles) * BN;
+      for (int u = u0; u < num_units; u += ustep) {
+        const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
+        const int n0 = (u % P.num_n_tiles) * BN;
         const int ns = tile_slabs(P, n0);
         const int o0 = P.act == ACT_GLU ? n0 / 2 : n0;
         for (int s = 0; s < ns; ++s) {
@@ -303,9 +348,9 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     uint32_t buf_phase = 0;
     int e = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x, seq = 0; tile < num_tiles; tile += gridDim.x, ++seq) {
-      const int m0 = (tile / P.num_n_tiles) * BM;
-      const int n0 = (tile % P.num_n_tiles) * BN;
+    for (int u = u0, seq = 0; u < num_units; u += ustep, ++seq) {
+      const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
+      const int n0 = (u % P.num_n_tiles) * BN;
       const int row = m0 + row_in_tile;
       unsigned mask_byte = 1u;   // loaded now, compared after the drains (off the critical path)
       if (row < P.m_rows && P.frame_mask) mask_byte = __ldg(P.frame_mask + row);
@@ -329,7 +374,10 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader's MMA thread waits
+          else mbar_arrive(&tempty_bar[buf]);
+        }
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
       }
       if (warp == 4 && lane == 0) JB_TRACE3(4, 0, seq);
@@ -419,11 +467,17 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // no CTA exits while its peer may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(TMEM_COLS))
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(TMEM_COLS))
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(TMEM_COLS))
+                   : "memory");
   }
 }
 
@@ -470,8 +524,12 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   const int halo_rows = round_up(BM + (p.taps - 1) * p.tap_stride, 8);
   JB_PROPAGATE(make_tmap(&ta_hi, p.a_hi, p.a_rows, a_cols, p.a_ld, halo_rows));
   JB_PROPAGATE(make_tmap(&ta_lo, p.a_lo, p.a_rows, a_cols, p.a_ld, halo_rows));
-  JB_PROPAGATE(make_tmap(&tb_hi, p.w_hi, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BN));
-  JB_PROPAGATE(make_tmap(&tb_lo, p.w_lo, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, BN));
+  // CTA pairs (cta_group::2): each SM is sent, stores and reads half of every weight tile pair, and the weight ring
+  // is twice as deep for the same bytes; needs >= 4 M tiles to be worth the lockstep
+  static const int env_pair = getenv("JATTS_B200_TC3_PAIR") ? atoi(getenv("JATTS_B200_TC3_PAIR")) : 1;
+  const bool pair = env_pair != 0 && ceil_div(p.m_rows, BM) >= 4;
+  JB_PROPAGATE(make_tmap(&tb_hi, p.w_hi, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, pair ? BN / 2 : BN));
+  JB_PROPAGATE(make_tmap(&tb_lo, p.w_lo, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, pair ? BN / 2 : BN));
   tres = tf32 = thi = tlo = ta_hi;
   if (e.res_f32) JB_PROPAGATE(make_tmap_f32(&tres, e.res_f32, p.m_rows, p.n, e.res_ld));
   if (e.out_f32) JB_PROPAGATE(make_tmap_f32(&tf32, e.out_f32, p.m_rows, p.n, e.out_f32_ld));
@@ -489,6 +547,7 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.m_rows = p.m_rows;
   kp.num_m_tiles = ceil_div(p.m_rows, BM);
   kp.num_n_tiles = p.n_pad / BN;
+  kp.num_groups = ceil_div(kp.num_m_tiles, 2) * kp.num_n_tiles;
   kp.frame_mask = p.frame_mask;
   kp.bias = e.bias;
   kp.act = e.act;
@@ -507,21 +566,36 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.entries = entries;
   kp.trace = g_trace_ptr;
   const int smem_bytes = SMEM_FIXED + entries * kp.entry_bytes;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    JB_CUDA_OK(cudaFuncSetAttribute(gemm_split_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes = smem_bytes;
+  static int attr_bytes[2] = {0, 0};
+  if (smem_bytes > attr_bytes[pair]) {
+    if (pair) JB_CUDA_OK(cudaFuncSetAttribute(gemm_split_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    else JB_CUDA_OK(cudaFuncSetAttribute(gemm_split_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_bytes[pair] = smem_bytes;
   }
-  const int tiles = kp.num_m_tiles * kp.num_n_tiles;
-  if (tiles == 0) return 0;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int units = pair ? kp.num_groups : kp.num_m_tiles * kp.num_n_tiles;
+  if (units == 0) return 0;
+  const int max_units = pair ? num_sms() / 2 : num_sms();
+  const int grid = (units < max_units ? units : max_units) * (pair ? 2 : 1);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventCreate(&e0));
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  gemm_split_tma_kernel<<<grid, kThreads3, smem_bytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp);
+  if (!pair) {
+    gemm_split_tma_kernel<false><<<grid, kThreads3, smem_bytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp);
+  } else {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads3);
+    lc.dynamicSmemBytes = smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    lc.attrs = la; lc.numAttrs = 1;
+    JB_CUDA_OK(cudaLaunchKernelEx(&lc, gemm_split_tma_kernel<true>, ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp));
+  }
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));
