@@ -227,6 +227,8 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   if (cl > 1) cluster_sync_all();   // peers' mbarriers are initialised before any multicast load / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel's prologue may start on SMs this grid has left
+  pdl_wait();                // everything above ran under the previous kernel's tail; its outputs are visible from here
 
   if (warp == 0) {
     // ===================== mainloop TMA producer =====================
@@ -725,20 +727,7 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  if (cl == 1) {
-    kern<<<grid, kThreads2, smem_bytes, stream>>>(ta, tb, tbm, tres, tacc, to0, to1, kp);
-  } else {
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(kThreads2);
-    lc.dynamicSmemBytes = smem_bytes;
-    lc.stream = stream;
-    cudaLaunchAttribute la[1];
-    la[0].id = cudaLaunchAttributeClusterDimension;
-    la[0].val.clusterDim.x = cl; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
-    lc.attrs = la; lc.numAttrs = 1;
-    JB_CUDA_OK(cudaLaunchKernelEx(&lc, kern, ta, tb, tbm, tres, tacc, to0, to1, kp));
-  }
+  JB_CUDA_OK(launch_tc(kern, grid, kThreads2, smem_bytes, stream, cl, ta, tb, tbm, tres, tacc, to0, to1, kp));
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));

@@ -181,6 +181,8 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   if constexpr (PAIR) cluster_sync_all();   // the peer's mbarriers exist before any remote arrive / pair load
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlapped the previous kernel's tail; its outputs are visible from here
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -582,20 +584,10 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  if (!pair) {
-    gemm_split_tma_kernel<false><<<grid, kThreads3, smem_bytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp);
-  } else {
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(kThreads3);
-    lc.dynamicSmemBytes = smem_bytes;
-    lc.stream = stream;
-    cudaLaunchAttribute la[1];
-    la[0].id = cudaLaunchAttributeClusterDimension;
-    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
-    lc.attrs = la; lc.numAttrs = 1;
-    JB_CUDA_OK(cudaLaunchKernelEx(&lc, gemm_split_tma_kernel<true>, ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp));
-  }
+  if (!pair)
+    JB_CUDA_OK(launch_tc(gemm_split_tma_kernel<false>, grid, kThreads3, smem_bytes, stream, 1, ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp));
+  else
+    JB_CUDA_OK(launch_tc(gemm_split_tma_kernel<true>, grid, kThreads3, smem_bytes, stream, 2, ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp));
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));

@@ -175,6 +175,8 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlapped the previous kernel's tail; its outputs are visible from here
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one activation slab per tile =====================
@@ -552,7 +554,7 @@ int launch_pair(const MrfPairProblem& p, cudaStream_t stream) {
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  kern<<<grid, kThreadsP, smem_bytes, stream>>>(ta, tw1, tw2, tout, kp);
+  JB_CUDA_OK(launch_tc(kern, grid, kThreadsP, smem_bytes, stream, 1, ta, tw1, tw2, tout, kp));
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));

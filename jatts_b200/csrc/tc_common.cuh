@@ -1,5 +1,6 @@
 // PTX wrappers (mbarrier, TMA, tcgen05) and tensor-map helpers shared by the tensor-core kernels.
 #pragma once
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -243,6 +244,40 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel's prologue (barrier init, TMEM allocation, descriptor prefetch, bias
+// staging) runs while the previous kernel of the stream drains its last tiles; pdl_wait() returns once that
+// kernel has completed and its writes are visible.  A kernel launched without the attribute sees both as no-ops.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// one launch path for the tensor-core kernels: optional cluster dimension, optional programmatic serialization
+template <typename Kern, typename... Args>
+inline cudaError_t launch_tc(Kern kern, int grid, int threads, int smem_bytes, cudaStream_t stream, int cluster, Args... args) {
+  static const int pdl = getenv("JATTS_B200_PDL") ? atoi(getenv("JATTS_B200_PDL")) : 1;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(threads);
+  lc.dynamicSmemBytes = smem_bytes;
+  lc.stream = stream;
+  cudaLaunchAttribute la[2];
+  int n = 0;
+  if (cluster > 1) {
+    la[n].id = cudaLaunchAttributeClusterDimension;
+    la[n].val.clusterDim.x = cluster; la[n].val.clusterDim.y = 1; la[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    la[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    la[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  lc.attrs = la;
+  lc.numAttrs = n;
+  return cudaLaunchKernelEx(&lc, kern, args...);
 }
 
 // ------------------------------------------------------------------------------------------------
