@@ -35,6 +35,12 @@ CASES = {
     "upsample_s3":     (dict(m=400, c_in=64, n=3 * 32, taps=2, tap_off0=0, tap_stride=-1, up_s=3, up_cout=32, block_n=32, out=("f32",)), 1e-4),
     "upsample_s4_bn256": (dict(m=300, c_in=128, n=4 * 64, taps=2, tap_off0=0, tap_stride=-1, up_s=4, up_cout=64, block_n=256, out=("f32",)), 1e-4),
     "persistent_wrap": (dict(m=128 * 160, c_in=64, n=128, taps=3, block_n=128, out=("hi",)), 1e-4),
+    # CTA-pair (cta_group::2) mode with an ODD number of M tiles: the second CTA of the last pair runs an empty tile
+    "pair_odd_tiles_c128": (dict(m=128 * 9 + 3, c_in=128, n=128, taps=7, dil=3, block_n=128, res="bf16", mask_rate=25, out=("hi", "act")), 1e-4),
+    "pair_odd_tiles_n256": (dict(m=128 * 5 + 77, c_in=256, n=256, taps=11, dil=1, block_n=128, accum="bf16", res="bf16", out=("act",)), 1e-4),
+    "pair_many_waves": (dict(m=128 * 148 * 3 + 128 * 3 + 9, c_in=128, n=128, taps=7, dil=5, block_n=128, act=A.ACT_LRELU, out=("hi",)), 1e-4),
+    "split_pair_odd_tiles": (dict(m=128 * 7 + 5, c_in=384, n=384, taps=3, split_mode=True, res="f32", scale=0.5, out=("f32", "hi", "lo")), 2e-5),
+    "split_pair_many_waves": (dict(m=128 * 148 * 2 + 128 * 5 + 1, c_in=128, n=256, taps=3, split_mode=True, act=A.ACT_RELU, out=("hi", "lo")), 2e-5),
 }
 
 

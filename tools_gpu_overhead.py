@@ -1,0 +1,23 @@
+"""Fixed per-launch cost of the fused residual-unit kernel: launches with T, 2T, 4T tiles per CTA (run under ncu)."""
+import ctypes as C
+import torch
+from jatts_b200 import _lib
+
+dev = "cuda"
+st = torch.cuda.current_stream().cuda_stream
+for c, k, d in ((32, 3, 1), (32, 11, 5), (64, 7, 3)):
+    for T in (10, 20, 40, 80):
+        rows = (128 - (k - 1)) * 148 * T
+        xa = torch.randn(rows, c, device=dev).to(torch.bfloat16)
+        w1 = (torch.randn(k, c, 64, device=dev) * 0.05).to(torch.bfloat16)
+        w2 = (torch.randn(k, c, 64, device=dev) * 0.05).to(torch.bfloat16)
+        b = torch.zeros(c, device=dev)
+        out = torch.empty_like(xa)
+        a = _lib.MrfPairArgs()
+        a.d_xa, a.rows, a.ld, a.c = xa.data_ptr(), rows, c, c
+        a.d_w1, a.d_w2, a.taps, a.n_pad, a.k_pad, a.dilation = w1.data_ptr(), w2.data_ptr(), k, c, 64, d
+        a.d_b1, a.d_b2, a.slope, a.rate = b.data_ptr(), b.data_ptr(), 0.1, 1
+        a.post_scale, a.out_slope, a.d_out, a.out_ld = 1.0, 0.1, out.data_ptr(), c
+        for _ in range(3):
+            _lib.check(_lib.lib.jatts_op_mrf_pair(C.byref(a), st))
+        torch.cuda.synchronize()
