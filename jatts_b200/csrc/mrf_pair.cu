@@ -55,6 +55,7 @@ struct PairParams {
   int slab_rows;      // rows loaded per tile
   int m_rows, num_tiles;
   int sa, nt, rb;     // activation slabs, t slabs, W2 ring depth (0 = W2 resident)
+  int la;             // conv1 look-ahead: conv1 of tile n+la is issued before conv2 of tile n (1..3); la+1 T accumulators
   int store_lag;      // 1: keep one TMA store in flight behind the newest (its slab is released one tile later)
   int leader_poll;    // 1: one warp per epilogue group polls the mbarriers, the others sleep in bar.sync
   int slab_bytes;     // bytes between activation slabs (slab_rows * row bytes rounded up to 1024)
@@ -94,7 +95,7 @@ struct CfgP {
   static constexpr int T_BYTES = kTRows * KROWB;
   static constexpr int B_BYTES = C * KROWB;              // one tap's [C x C] weight tile
   static constexpr int TAIL_BYTES = 2048;                // biases (2*C floats) + barriers
-  static constexpr int TMEM_COLS = 4 * C;                // 128 / 256
+  static constexpr int TMEM_COLS = 8 * C;                // T[<= 4] | U[2] accumulators of C columns (6 C used): 256 / 512
   static_assert(A_SLAB_BYTES % 1024 == 0 && T_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle alignment");
 };
 
@@ -120,9 +121,9 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint64_t* xa_full = bars;                 // [4]
   uint64_t* xa_empty = xa_full + kMaxSA;    // [4]
   uint64_t* out_ready = xa_empty + kMaxSA;  // [4]
-  uint64_t* T_full = out_ready + kMaxSA;    // [2]
-  uint64_t* T_empty = T_full + 2;           // [2]
-  uint64_t* U_full = T_empty + 2;           // [2]
+  uint64_t* T_full = out_ready + kMaxSA;    // [4]
+  uint64_t* T_empty = T_full + 4;           // [4]
+  uint64_t* U_full = T_empty + 4;           // [2]
   uint64_t* U_empty = U_full + 2;           // [2]
   uint64_t* t_full = U_empty + 2;           // [2]
   uint64_t* t_empty = t_full + 2;           // [2]
@@ -146,9 +147,11 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_init(&xa_empty[i], 1);
       mbar_init(&out_ready[i], 4);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&T_full[i], 1);
       mbar_init(&T_empty[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&U_full[i], 1);
       mbar_init(&U_empty[i], 4);
       mbar_init(&t_full[i], 4);
@@ -216,16 +219,20 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       constexpr uint32_t desc_hi = static_cast<uint32_t>((8 * K::KROWB) >> 4) | (1u << 14) | (static_cast<uint32_t>(C == 64 ? 2 : 4) << 29);
       const uint32_t w1_addr = smem_u32(w1_base), w2_addr = smem_u32(w2_base);
       const uint32_t slab_addr = smem_u32(slab_base), t_addr = smem_u32(t_base);
-      Ring ra(P.sa), rt(P.nt), rb(stream_w2 ? P.rb : 1);
+      Ring ra(P.sa), rt(P.nt), rb(stream_w2 ? P.rb : 1), rT(P.la + 1);
       mbar_wait(w_full, 0);
       tc_fence_after();
-      for (int i = 0; i <= my_tiles; ++i) {
+      // Issue order C1(0..la-1), then C1(n+la), C2(n) alternately: E1 of tile n (accumulator hand-off, conversion,
+      // fence, hand-back: ~1.7-2.7 k clk) has la conv1 phases plus a conv2 phase of tensor-pipe work to hide behind.
+      // With la = 1 the pipe idled (E1 chain - C1 time) per tile: measured periods 1441 / 2950 (C=32 k=3 / 11) and
+      // 4644 (C=64 k=7) against 540 / 1971 / 2688 clk of MMA time.
+      for (int i = 0; i < my_tiles + P.la; ++i) {
         if (i < my_tiles) {
-          // ---- conv1 of tile i -> T[i & 1]
-          const int b = i & 1;
+          // ---- conv1 of tile i -> T[i % (la+1)]
+          const int b = rT.idx;
           mbar_wait(&xa_full[ra.idx], ra.phase);
           PT(1, 4, i);
-          mbar_wait(&T_empty[b], ((i >> 1) & 1) ^ 1);
+          mbar_wait(&T_empty[b], rT.phase ^ 1);
           PT(1, 0, i);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(b * C);
@@ -245,16 +252,17 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           tc_commit(&T_full[b]);
           PT(1, 1, i);
           ra.next();
+          rT.next();
         }
-        if (i >= 1) {
-          // ---- conv2 of tile i-1 -> U[(i-1) & 1]
-          const int m = i - 1, b = m & 1;
+        if (i >= P.la) {
+          // ---- conv2 of tile i-la -> U[(i-la) & 1]
+          const int m = i - P.la, b = m & 1;
           mbar_wait(&t_full[rt.idx], rt.phase);
           PT(1, 5, m);
           mbar_wait(&U_empty[b], ((m >> 1) & 1) ^ 1);
           PT(1, 2, m);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(2 * C + b * C);
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(4 * C + b * C);
           const uint32_t a0 = t_addr + static_cast<uint32_t>(rt.idx * K::T_BYTES);
 #pragma unroll
           for (int tap = 0; tap < TAPS; ++tap) {
@@ -314,12 +322,19 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int grp = (warp - 4) >> 2;
     const int lane_group = warp & 3;
     const int row = lane_group * 32 + lane;                   // t row of this thread
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + static_cast<uint32_t>(grp * C);
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
     const uint32_t row_off = static_cast<uint32_t>(row) * K::KROWB;
     const uint32_t sw = swz<C>(row);
     const int tb = P.nt == 2 ? grp : 0;                       // t slab (and its barriers) of this group
     uint32_t n_done = 0;                                      // tiles this group has processed
+    Ring rT(P.la + 1);                                        // T accumulator of tile i: i % (la+1)
+    if (grp) rT.next();
     for (int i = grp; i < my_tiles; i += 2, ++n_done) {
+      const int tbuf = rT.idx;
+      const uint32_t tphase = rT.phase;
+      rT.next();
+      rT.next();
+      const uint32_t lane_addr = lane_base + static_cast<uint32_t>(tbuf * C);
       const int tile = blockIdx.x + i * gridDim.x;
       const int g = tile * P.out_m - P.h2 + row;
       float keep = 0.f;
@@ -327,7 +342,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       // one warp of the group polls the mbarriers, the other three sleep in bar.sync (a polling warp takes
       // issue slots from the warps doing the math: 20 warps share 4 schedulers)
       if (!P.leader_poll || lane_group == grp) {
-        mbar_wait(&T_full[grp], n_done & 1);
+        mbar_wait(&T_full[tbuf], tphase);
         // t slab free: conv2 of the tile that used it last has been committed (nt == 1: the previous tile, i-1)
         mbar_wait(&t_empty[tb], ((P.nt == 2 ? n_done : static_cast<uint32_t>(i)) & 1) ^ 1);
       }
@@ -345,7 +360,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (s == C / 32 - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&T_empty[grp]);
+          if (lane == 0) mbar_arrive(&T_empty[tbuf]);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -373,7 +388,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int grp = (warp - 12) >> 2;
     const int lane_group = warp & 3;
     const int row = lane_group * 32 + lane;                   // output row of this thread within the tile
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + static_cast<uint32_t>(2 * C + grp * C);
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + static_cast<uint32_t>(4 * C + grp * C);
     const int srow = row + P.halo + P.pad;                    // slab row holding x[row] (and receiving out[row])
     const uint32_t row_off = static_cast<uint32_t>(srow) * K::KROWB;
     const uint32_t sw = swz<C>(srow);
@@ -529,6 +544,15 @@ int launch_pair(const MrfPairProblem& p, cudaStream_t stream) {
   if (sa > kMaxSA) sa = kMaxSA;
   if (force_sa > 1 && force_sa < sa) sa = force_sa;
   kp.sa = sa;
+  static const int env_la = getenv("JATTS_B200_PAIR_LA") ? atoi(getenv("JATTS_B200_PAIR_LA")) : 0;
+  // a slab is held from its load until the tile's store, so la + 1 tiles are in use when conv1 of the next one
+  // needs its slab: la <= sa - 2 (more would deadlock the producer against the store)
+  // measured: la = 2 pays at C = 64 (k = 3: 213 -> 190 us, k = 7: 421 -> 370 us per launch), nothing at C = 32
+  kp.la = C == 64 ? 2 : 1;
+  if (env_la >= 1) kp.la = env_la;
+  if (kp.la > sa - 2) kp.la = sa - 2;
+  if (kp.la > 3) kp.la = 3;
+  if (kp.la < 1) kp.la = 1;
   kp.store_lag = env_lag >= 0 ? env_lag : (sa >= 6 ? 1 : 0);
   kp.leader_poll = env_poll >= 0 ? env_poll : 1;
   kp.slab_bytes = slab_bytes;
