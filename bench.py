@@ -127,7 +127,7 @@ class ClockSampler:
 
 def measured_traffic():
     """DRAM bytes (read + write) of the dominant kernel family per step, from the committed ncu capture
-    (profiles/r01_traffic.json, written by tools_step_metrics.py); None when the file is absent."""
+    (profiles/r01_traffic.json, written by tools/step_metrics.py); None when the file is absent."""
     p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.isfile(p):
         with open(p) as f:

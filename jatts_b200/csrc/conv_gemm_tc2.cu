@@ -301,7 +301,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // Measured (tools_gpu_trace.py): for N <= 64 this single issuing thread is the bottleneck -- ~46 clk to
+    // Measured (tools/gpu_trace.py): for N <= 64 this single issuing thread is the bottleneck -- ~46 clk to
     // issue one tcgen05.mma that executes in 16-32 clk, plus several hundred clk of mbarrier handling per
     // tile.  A second issuing warp made it worse (84 clk per MMA: the issue port is shared).  Tiles alternate
     // between the two TMEM accumulators / epilogue groups.

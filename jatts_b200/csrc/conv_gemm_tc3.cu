@@ -21,7 +21,7 @@
 //
 // The first version of this path (conv_gemm_tc_kernel<128, true>) had the same mainloop but finished
 // tiles with per-thread global loads/stores: measured 52 k clk to store one 128x128 tile against 10-14 k
-// clk of MMA work (tools_gpu_trace1.py).
+// clk of MMA work (tools/gpu_trace1.py).
 #include <cstdlib>
 
 #include "conv_gemm.cuh"

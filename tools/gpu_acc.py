@@ -1,7 +1,9 @@
 """Diagnostic: fp32 accumulation behaviour of tcgen05.mma (bias / spread vs K)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import sys, zlib
 import torch
-sys.path.insert(0, "tests")
+sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tests"))
 from gemm_ref import Case
 
 for positive in (False, True):

@@ -1,5 +1,7 @@
 """First-contact diagnostic for the GPU box: run every conv-GEMM case on both implementations and
 print the error table (does not stop at the first failure).  Not part of the product or the tests."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import sys
 import time
 import traceback
@@ -7,7 +9,7 @@ import zlib
 
 import torch
 
-sys.path.insert(0, "tests")
+sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tests"))
 from gemm_ref import Case  # noqa: E402
 from test_ops_gpu import CASES  # noqa: E402
 

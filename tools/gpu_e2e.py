@@ -1,4 +1,6 @@
 """First-contact end-to-end diagnostic (GPU box): CUDA path vs the CPU oracle, verbose."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import sys
 import time
 

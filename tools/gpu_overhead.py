@@ -1,4 +1,6 @@
 """Fixed per-launch cost of the fused residual-unit kernel: launches with T, 2T, 4T tiles per CTA (run under ncu)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import ctypes as C
 import torch
 from jatts_b200 import _lib

@@ -1,4 +1,6 @@
 """Diagnostic: mel / pitch error statistics of the CUDA FS2 path vs the fp32 oracle over several utterances."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import os, sys, torch
 import jatts_b200
 from oracle import fs2 as ofs2, recipes

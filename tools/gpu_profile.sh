@@ -1,11 +1,11 @@
 #!/bin/bash
 # Round profiles: (1) per-launch metrics of one whole step, (2) --set full captures of the dominant kernels.
-# usage (under gpurun): ./tools_gpu_profile.sh TAG
+# usage (under gpurun): ./tools/gpu_profile.sh TAG
 TAG=${1:-r01}
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.max,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum
-timeout 900 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_step_metrics.csv python tools_profile_step.py all > /dev/null 2>&1
+timeout 900 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_step_metrics.csv python tools/profile_step.py all > /dev/null 2>&1
 full() {  # name, step part, kernel regex, skip
-  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$3 -s $4 -c 1 -f -o gpurun_out/${TAG}_full_$1 python tools_profile_step.py $2 > /dev/null 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$3 -s $4 -c 1 -f -o gpurun_out/${TAG}_full_$1 python tools/profile_step.py $2 > /dev/null 2>&1
   ncu -i gpurun_out/${TAG}_full_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_$1.raw.csv 2>/dev/null
 }
 full pair_c32_k11 voc mrf_pair_kernel 16

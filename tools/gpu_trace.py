@@ -1,6 +1,8 @@
 """Debug: per-role timeline of CTA 0 for one big conv launch (C=32 conv2-like)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import sys, torch
-sys.path.insert(0, "tests")
+sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tests"))
 from gemm_ref import Case
 from jatts_b200 import _lib
 c, k, dil = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])

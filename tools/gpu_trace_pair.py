@@ -1,4 +1,6 @@
 """Debug: per-role clock64 timeline of CTA 0 of the fused residual-unit kernel (mrf_pair.cu) on one big launch."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import ctypes as C
 import sys
 import torch

@@ -1,4 +1,6 @@
 """Aggregate an ncu `--metrics gpu__time_duration.sum --csv` launch list per kernel (and list every launch with -v)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import collections
 import csv
 import re

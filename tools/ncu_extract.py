@@ -1,4 +1,6 @@
 """Pull the judged metrics out of an `ncu --page raw --csv` dump (one kernel) into a small metric,unit,value csv."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import csv
 import sys
 

@@ -1,4 +1,6 @@
 """One warm-up + one profiled step of the bench workload (run under ncu; not a bench)."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import sys
 import torch
 import jatts_b200

@@ -1,5 +1,7 @@
-"""Summarise an ncu per-launch metrics csv of one step (tools_gpu_profile.sh) per kernel family:
+"""Summarise an ncu per-launch metrics csv of one step (tools/gpu_profile.sh) per kernel family:
 time, DRAM bytes, tensor-pipe activity.  Writes a markdown table and (optionally) the traffic json bench.py reads."""
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))  # repo root
 import collections
 import csv
 import json
@@ -58,4 +60,4 @@ if len(sys.argv) > 2:
     json.dump({"hifigan_conv_dram_bytes_per_step": a["rd"] + a["wr"], "launches": a["n"], "ms_under_ncu": a["t"] * 1e3,
                "tensor_pipe_active_pct_time_weighted": a["tensor_w"] / a["t"],
                "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over every HiFi-GAN convolution launch of one "
-                         "bench step (tools_gpu_profile.sh -> " + sys.argv[1].split("/")[-1] + ")"}, open(sys.argv[2], "w"), indent=1)
+                         "bench step (tools/gpu_profile.sh -> " + sys.argv[1].split("/")[-1] + ")"}, open(sys.argv[2], "w"), indent=1)
