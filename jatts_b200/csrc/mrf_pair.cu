@@ -55,6 +55,8 @@ struct PairParams {
   int slab_rows;      // rows loaded per tile
   int m_rows, num_tiles;
   int sa, nt, rb;     // activation slabs, t slabs, W2 ring depth (0 = W2 resident)
+  int dbg;            // debug (JATTS_B200_PAIR_DEBUG, results are WRONG): 1 = epilogues skip their shared-memory traffic,
+                      // 2 = also skip the TMEM loads; isolates the MMA/TMA pipeline from the epilogue work in timelines
   int la;             // conv1 look-ahead: conv1 of tile n+la is issued before conv2 of tile n (1..3); la+1 T accumulators
   int store_lag;      // 1: keep one TMA store in flight behind the newest (its slab is released one tile later)
   int leader_poll;    // 1: one warp per epilogue group polls the mbarriers, the others sleep in bar.sync
@@ -224,8 +226,11 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       tc_fence_after();
       // Issue order C1(0..la-1), then C1(n+la), C2(n) alternately: E1 of tile n (accumulator hand-off, conversion,
       // fence, hand-back: ~1.7-2.7 k clk) has la conv1 phases plus a conv2 phase of tensor-pipe work to hide behind.
-      // With la = 1 the pipe idled (E1 chain - C1 time) per tile: measured periods 1441 / 2950 (C=32 k=3 / 11) and
-      // 4644 (C=64 k=7) against 540 / 1971 / 2688 clk of MMA time.
+      // Measured with the epilogue work disabled (JATTS_B200_PAIR_DEBUG=1): the MMAs run at the SS rate (44 clk at
+      // N = 32) but every phase switch (commit, two mbarrier polls, fence, descriptor set-up: ~190 clk, 4 per tile)
+      // is idle tensor-pipe time because the issue queue is only 1-2 instructions deep: 2700 clk per tile at k = 11
+      // against 1971 clk of MMAs.  Probing the next phase's barriers before the last tap (mbarrier.test_wait) made
+      // every shape 3-15 % slower and was dropped.
       for (int i = 0; i < my_tiles + P.la; ++i) {
         if (i < my_tiles) {
           // ---- conv1 of tile i -> T[i % (la+1)]
@@ -354,14 +359,20 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
       for (int s = 0; s < C / 32; ++s) {
         uint32_t r[32];
-        tmem_ld32(lane_addr + static_cast<uint32_t>(s * 32), r);
-        tmem_ld_wait();
+        if (P.dbg < 2) {
+          tmem_ld32(lane_addr + static_cast<uint32_t>(s * 32), r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) r[q] = 0u;
+        }
         if (s == 0 && lane_group == 0 && lane == 0) PT(2, 3, i);
         if (s == C / 32 - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&T_empty[tbuf]);
         }
+        if (P.dbg) continue;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float v[8];
@@ -424,15 +435,20 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
       for (int s = 0; s < C / 32; ++s) {
         uint32_t r[32];
-        tmem_ld32(lane_addr + static_cast<uint32_t>(s * 32), r);
-        tmem_ld_wait();
+        if (P.dbg < 2) {
+          tmem_ld32(lane_addr + static_cast<uint32_t>(s * 32), r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) r[q] = 0u;
+        }
         if (s == 0 && lane_group == 0 && lane == 0) PT(3, 2, i);
         if (s == C / 32 - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&U_empty[grp]);
         }
-        if (active) {
+        if (active && !P.dbg) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t p = srow_p + ((static_cast<uint32_t>(s * 4 + c) ^ sw) << 4);
@@ -513,6 +529,8 @@ int launch_pair(const MrfPairProblem& p, cudaStream_t stream) {
   kp.acc = p.accum;
   kp.acc_ld = p.accum_ld;
   kp.trace = g_trace_ptr;
+  static const int env_dbg = getenv("JATTS_B200_PAIR_DEBUG") ? atoi(getenv("JATTS_B200_PAIR_DEBUG")) : 0;
+  kp.dbg = env_dbg;
   JB_REQUIRE(kp.slab_rows <= K::SLAB_CAP && kp.slab_rows <= 256, JATTS_E_UNSUPPORTED, "mrf_pair: receptive field too wide");
   JB_REQUIRE(kp.h2 + kTileM <= kTRows, JATTS_E_UNSUPPORTED, "mrf_pair: kernel size too large");
   // shared memory plan: everything resident with as many activation slabs as fit (a slab lives from its TMA load
