@@ -41,7 +41,7 @@ extern long long* g_trace_ptr;   // conv_gemm_tc2.cu
 
 namespace {
 
-constexpr int kThreadsP = 640;   // 4 control warps + 2 x 4 E1 warps + 2 x 4 E2 warps
+constexpr int kThreadsP = 640;   // 4 control warps (producer, conv1 issuer, store, conv2 issuer) + 2 x 4 E1 + 2 x 4 E2 warps
 constexpr int kTileM = 128;
 constexpr int kTRows = 144;   // t slab rows: 128 written + 16 zero rows read by the shifted conv2 taps (k <= 17)
 constexpr int kMaxSA = 8, kMaxRB = 8;
@@ -57,6 +57,7 @@ struct PairParams {
   int sa, nt, rb;     // activation slabs, t slabs, W2 ring depth (0 = W2 resident)
   int dbg;            // debug (JATTS_B200_PAIR_DEBUG, results are WRONG): 1 = epilogues skip their shared-memory traffic,
                       // 2 = also skip the TMEM loads; isolates the MMA/TMA pipeline from the epilogue work in timelines
+  int dual;           // 1: conv1 phases are issued by warp 1, conv2 phases by warp 3 (two issuing threads; W2 resident only)
   int la;             // conv1 look-ahead: conv1 of tile n+la is issued before conv2 of tile n (1..3); la+1 T accumulators
   int store_lag;      // 1: keep one TMA store in flight behind the newest (its slab is released one tile later)
   int leader_poll;    // 1: one warp per epilogue group polls the mbarriers, the others sleep in bar.sync
@@ -201,18 +202,6 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         ra.next();
       }
     }
-  } else if (warp == 3) {
-    // ===================== conv2 weight ring (only when W2 is not resident) =====================
-    if (stream_w2 && elect_one()) {
-      Ring rb(P.rb);
-      for (int i = 0; i < my_tiles; ++i)
-        for (int tap = 0; tap < P.taps; ++tap) {
-          mbar_wait(&w2_empty[rb.idx], rb.phase ^ 1);
-          mbar_expect_tx(&w2_full[rb.idx], K::B_BYTES);
-          tma_load_2d(&tm_w2, &w2_full[rb.idx], w2_base + rb.idx * K::B_BYTES, 0, tap * P.w_rows_per_tap);
-          rb.next();
-        }
-    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
@@ -259,7 +248,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           ra.next();
           rT.next();
         }
-        if (i >= P.la) {
+        if (i >= P.la && !P.dual) {
           // ---- conv2 of tile i-la -> U[(i-la) & 1]
           const int m = i - P.la, b = m & 1;
           mbar_wait(&t_full[rt.idx], rt.phase);
@@ -321,6 +310,66 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         ra.next();
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else if (warp == 3) {
+    if (stream_w2) {
+      // ===================== conv2 weight ring (W2 not resident: warp 1 issues both convolutions) =====================
+      if (elect_one()) {
+        Ring rb(P.rb);
+        for (int i = 0; i < my_tiles; ++i)
+          for (int tap = 0; tap < P.taps; ++tap) {
+            mbar_wait(&w2_empty[rb.idx], rb.phase ^ 1);
+            mbar_expect_tx(&w2_full[rb.idx], K::B_BYTES);
+            tma_load_2d(&tm_w2, &w2_full[rb.idx], w2_base + rb.idx * K::B_BYTES, 0, tap * P.w_rows_per_tap);
+            rb.next();
+          }
+      }
+    } else if (P.dual && elect_one()) {
+      // ===================== second MMA issuer: every conv2 phase (W2 resident) =====================
+      // While one issuing thread is between phases (commit, mbarrier polls, fence, descriptor set-up: ~190 clk with a
+      // 1-2 deep issue queue) the other one's MMAs keep the tensor pipe busy; the two only meet on the pipe itself.
+      // Measured per launch (us): C=32 k=3/7/11 285/453/738 -> 249/350/390, C=64 k=3/7 218/379 -> 153/268.
+      constexpr uint32_t idesc = make_idesc(kTileM, C, /*is_bf16=*/true);
+      constexpr uint32_t desc_lo0 = 1u << 16;
+      constexpr uint32_t desc_hi = static_cast<uint32_t>((8 * K::KROWB) >> 4) | (1u << 14) | (static_cast<uint32_t>(C == 64 ? 2 : 4) << 29);
+      const uint32_t w2_addr = smem_u32(w2_base), t_addr = smem_u32(t_base);
+      Ring rt(P.nt), rb(stream_w2 ? P.rb : 1);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      for (int m = 0; m < my_tiles; ++m) {
+        const int b = m & 1;
+        mbar_wait(&t_full[rt.idx], rt.phase);
+        PT(1, 5, m);
+        mbar_wait(&U_empty[b], ((m >> 1) & 1) ^ 1);
+        PT(1, 2, m);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(4 * C + b * C);
+        const uint32_t a0 = t_addr + static_cast<uint32_t>(rt.idx * K::T_BYTES);
+#pragma unroll
+        for (int tap = 0; tap < TAPS; ++tap) {
+          uint32_t b_addr;
+          if (stream_w2) {
+            mbar_wait(&w2_full[rb.idx], rb.phase);
+            tc_fence_after();
+            b_addr = w2_addr + static_cast<uint32_t>(rb.idx) * K::B_BYTES;
+          } else {
+            b_addr = w2_addr + static_cast<uint32_t>(tap) * K::B_BYTES;
+          }
+          const uint32_t a_lo = desc_lo0 + ((a0 + static_cast<uint32_t>(tap) * K::KROWB) >> 4);
+          const uint32_t b_lo = desc_lo0 + (b_addr >> 4);
+#pragma unroll
+          for (int k = 0; k < K::KSTEPS; ++k)
+            tc_mma_bf16_lohi(tmem_d, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (tap | k) != 0 ? 1u : 0u);
+          if (stream_w2) {
+            tc_commit(&w2_empty[rb.idx]);
+            rb.next();
+          }
+        }
+        tc_commit(&U_full[b]);
+        tc_commit(&t_empty[rt.idx]);
+        PT(1, 3, m);
+        rt.next();
+      }
     }
   } else if (warp < 12) {
     // ===================== E1 (group = tile parity): T -> t slab (bf16, swizzled K-major) =====================
@@ -562,6 +611,8 @@ int launch_pair(const MrfPairProblem& p, cudaStream_t stream) {
   if (sa > kMaxSA) sa = kMaxSA;
   if (force_sa > 1 && force_sa < sa) sa = force_sa;
   kp.sa = sa;
+  static const int env_dual = getenv("JATTS_B200_PAIR_DUAL") ? atoi(getenv("JATTS_B200_PAIR_DUAL")) : 1;
+  kp.dual = (env_dual && rb == 0) ? 1 : 0;   // with a streamed W2 warp 3 is the weight producer: single issuer
   static const int env_la = getenv("JATTS_B200_PAIR_LA") ? atoi(getenv("JATTS_B200_PAIR_LA")) : 0;
   // a slab is held from its load until the tile's store, so la + 1 tiles are in use when conv1 of the next one
   // needs its slab: la <= sa - 2 (more would deadlock the producer against the store)
