@@ -13,6 +13,7 @@ import torch
 
 BN_EPS = 1e-5
 PE_MAX_LEN = 5000  # jatts/modules/positional_encoding.py:212 (initial max_len of the legacy table)
+GAP_ROWS = 8       # zero rows between utterances of the packed layout (csrc/common.cuh kGapRows)
 
 
 def round_up(a: int, b: int) -> int:

@@ -20,6 +20,8 @@ typedef __nv_bfloat16 bf16;
 extern long long g_launch_count;
 void set_last_error(const std::string& msg);
 const char* get_last_error();
+// opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (cached per device and kernel)
+int ensure_dynamic_smem(const void* kernel, int bytes);
 
 #define JB_CUDA_OK(expr)                                                                          \
   do {                                                                                            \

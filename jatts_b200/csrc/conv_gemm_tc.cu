@@ -502,11 +502,7 @@ static int launch(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.up_cout = p.up_cout > 0 ? p.up_cout : 1;
   kp.ep = p.ep;
   auto kern = conv_gemm_tc_kernel<BLOCK_N, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::SMEM_BYTES));
   const int tiles = kp.num_m_tiles * kp.num_n_tiles;
   if (tiles == 0) return 0;
   const int grid = tiles < num_sms() ? tiles : num_sms();

@@ -695,11 +695,7 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   if (sd_env) kp.store_depth = atoi(sd_env) < entries - 1 ? atoi(sd_env) : entries - 2;
   const int smem_bytes = C::SMEM_FIXED + w_bytes + entries * entry;
   auto kern = conv_bf16_tma_kernel<BLOCK_N, KCH, MODE, PAIR>;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes = smem_bytes;
-  }
+  JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_bytes));
   if (kp.num_groups == 0) return 0;
   int max_clusters = num_sms() / cl;
   if (cl > 2) {

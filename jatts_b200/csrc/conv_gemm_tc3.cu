@@ -568,12 +568,8 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.entries = entries;
   kp.trace = g_trace_ptr;
   const int smem_bytes = SMEM_FIXED + entries * kp.entry_bytes;
-  static int attr_bytes[2] = {0, 0};
-  if (smem_bytes > attr_bytes[pair]) {
-    if (pair) JB_CUDA_OK(cudaFuncSetAttribute(gemm_split_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    else JB_CUDA_OK(cudaFuncSetAttribute(gemm_split_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes[pair] = smem_bytes;
-  }
+  JB_PROPAGATE(ensure_dynamic_smem(pair ? reinterpret_cast<const void*>(gemm_split_tma_kernel<true>)
+                                        : reinterpret_cast<const void*>(gemm_split_tma_kernel<false>), smem_bytes));
   const int units = pair ? kp.num_groups : kp.num_m_tiles * kp.num_n_tiles;
   if (units == 0) return 0;
   const int max_units = pair ? num_sms() / 2 : num_sms();

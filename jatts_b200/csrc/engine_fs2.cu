@@ -322,6 +322,14 @@ extern "C" int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor*
   JB_REQUIRE(cfg->max_len > 0 && cfg->max_len <= 5000, JATTS_E_INVALID, "max_len must be in (0, 5000]");
   JB_REQUIRE(cfg->dur_layers >= 1 && cfg->pitch_layers >= 1 && cfg->energy_layers >= 1, JATTS_E_UNSUPPORTED,
              "predictors need >= 1 layer");
+  // "same" convolutions over the packed layout rely on the kGapRows zero rows between utterances: an even kernel
+  // would be centred differently from the reference's padding=(k-1)//2 and a half width above the gap would read
+  // the neighbouring utterance (the depthwise convolution bounds its taps per utterance and has no such limit)
+  for (int k : {cfg->ffn_kernel, cfg->dur_kernel, cfg->pitch_kernel, cfg->energy_kernel, cfg->postnet_filts})
+    JB_REQUIRE(k >= 1 && (k & 1) == 1 && (k - 1) / 2 <= kGapRows, JATTS_E_UNSUPPORTED,
+               "convolution kernel sizes must be odd with (k-1)/2 <= 8 (gap rows of the packed layout)");
+  JB_REQUIRE((cfg->enc_cnn_kernel & 1) == 1 && (cfg->dec_cnn_kernel & 1) == 1, JATTS_E_UNSUPPORTED,
+             "conformer depthwise kernel sizes must be odd");
   jatts_fs2* h = new jatts_fs2();
   h->cfg = *cfg;
   h->d_small = nullptr; h->d_nframes = nullptr;
@@ -434,23 +442,25 @@ extern "C" int jatts_fs2_run(jatts_fs2* h, float* d_mel, int64_t* d_durations, f
   if (h->frame.n_rows > h->cap_rows) {
     // growing the arena would drop phase-1 state (hs, cum, pitch/energy): keep them across the move
     const int tr = h->text.n_rows;
-    float *hs2, *sp2, *se2; int* cum2;
-    JB_CUDA_OK(cudaMalloc(&hs2, sizeof(float) * tr * d));
-    JB_CUDA_OK(cudaMalloc(&sp2, sizeof(float) * tr));
-    JB_CUDA_OK(cudaMalloc(&se2, sizeof(float) * tr));
-    JB_CUDA_OK(cudaMalloc(&cum2, sizeof(int) * tr));
-    JB_CUDA_OK(cudaMemcpyAsync(hs2, h->hs, sizeof(float) * tr * d, cudaMemcpyDeviceToDevice, s));
-    JB_CUDA_OK(cudaMemcpyAsync(sp2, h->s_pitch, sizeof(float) * tr, cudaMemcpyDeviceToDevice, s));
-    JB_CUDA_OK(cudaMemcpyAsync(se2, h->s_energy, sizeof(float) * tr, cudaMemcpyDeviceToDevice, s));
-    JB_CUDA_OK(cudaMemcpyAsync(cum2, h->cum, sizeof(int) * tr, cudaMemcpyDeviceToDevice, s));
-    JB_CUDA_OK(cudaStreamSynchronize(s));
+    struct Keep {   // frees on every exit path (an early JB_CUDA_OK return used to leak the four buffers)
+      float *hs = nullptr, *sp = nullptr, *se = nullptr; int* cum = nullptr;
+      ~Keep() { cudaFree(hs); cudaFree(sp); cudaFree(se); cudaFree(cum); }
+    } k;
+    JB_CUDA_OK(cudaMalloc(&k.hs, sizeof(float) * tr * d));
+    JB_CUDA_OK(cudaMalloc(&k.sp, sizeof(float) * tr));
+    JB_CUDA_OK(cudaMalloc(&k.se, sizeof(float) * tr));
+    JB_CUDA_OK(cudaMalloc(&k.cum, sizeof(int) * tr));
+    JB_CUDA_OK(cudaMemcpyAsync(k.hs, h->hs, sizeof(float) * tr * d, cudaMemcpyDeviceToDevice, s));
+    JB_CUDA_OK(cudaMemcpyAsync(k.sp, h->s_pitch, sizeof(float) * tr, cudaMemcpyDeviceToDevice, s));
+    JB_CUDA_OK(cudaMemcpyAsync(k.se, h->s_energy, sizeof(float) * tr, cudaMemcpyDeviceToDevice, s));
+    JB_CUDA_OK(cudaMemcpyAsync(k.cum, h->cum, sizeof(int) * tr, cudaMemcpyDeviceToDevice, s));
+    JB_CUDA_OK(cudaStreamSynchronize(s));   // the old arena is freed by the reserve below
     JB_PROPAGATE(ensure_workspace(h, h->frame.n_rows, h->n_utt, text_total));
-    JB_CUDA_OK(cudaMemcpyAsync(h->hs, hs2, sizeof(float) * tr * d, cudaMemcpyDeviceToDevice, s));
-    JB_CUDA_OK(cudaMemcpyAsync(h->s_pitch, sp2, sizeof(float) * tr, cudaMemcpyDeviceToDevice, s));
-    JB_CUDA_OK(cudaMemcpyAsync(h->s_energy, se2, sizeof(float) * tr, cudaMemcpyDeviceToDevice, s));
-    JB_CUDA_OK(cudaMemcpyAsync(h->cum, cum2, sizeof(int) * tr, cudaMemcpyDeviceToDevice, s));
-    JB_CUDA_OK(cudaStreamSynchronize(s));
-    cudaFree(hs2); cudaFree(sp2); cudaFree(se2); cudaFree(cum2);
+    JB_CUDA_OK(cudaMemcpyAsync(h->hs, k.hs, sizeof(float) * tr * d, cudaMemcpyDeviceToDevice, s));
+    JB_CUDA_OK(cudaMemcpyAsync(h->s_pitch, k.sp, sizeof(float) * tr, cudaMemcpyDeviceToDevice, s));
+    JB_CUDA_OK(cudaMemcpyAsync(h->s_energy, k.se, sizeof(float) * tr, cudaMemcpyDeviceToDevice, s));
+    JB_CUDA_OK(cudaMemcpyAsync(h->cum, k.cum, sizeof(int) * tr, cudaMemcpyDeviceToDevice, s));
+    JB_CUDA_OK(cudaStreamSynchronize(s));   // the temporaries are freed when `k` leaves scope
   }
   // The text-level layout tables (phase 0) stay valid; the text mask/seg arrays are about to be
   // overwritten by the frame layout, so the regulator only uses seg_start/seg_len of the text layout.

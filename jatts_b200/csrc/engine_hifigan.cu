@@ -120,6 +120,8 @@ extern "C" int jatts_hifigan_create(const jatts_hifigan_config* cfg, const jatts
   JB_REQUIRE(cfg->channels % (1 << cfg->n_upsamples) == 0 && (cfg->channels >> cfg->n_upsamples) % 32 == 0,
              JATTS_E_UNSUPPORTED, "every stage needs a channel count that is a multiple of 32");
   JB_REQUIRE((cfg->kernel_size & 1) == 1, JATTS_E_UNSUPPORTED, "kernel_size must be odd");
+  JB_REQUIRE(cfg->lrelu_slope > 0.f && cfg->lrelu_slope <= 1.f, JATTS_E_UNSUPPORTED,
+             "lrelu_slope must be in (0, 1] (activations are stored as LeakyReLU(x) and inverted with 1/slope)");
   jatts_hifigan* h = new jatts_hifigan();
   h->cfg = *cfg;
   auto fail = [&](int rc) { delete h; return rc; };

@@ -971,6 +971,14 @@ int add_speaker(const float* spembs, int spk_dim, const float* w, const float* b
 // ------------------------------------------------------------------------------------------------
 // durations + per-utterance inclusive scan (one warp per utterance)
 // ------------------------------------------------------------------------------------------------
+// A huge or infinite log-duration (bad checkpoint) must not wrap the int32 frame count into [0, max_len]: per-token
+// counts are clamped to 2^20 and totals saturate at 2^30 (32 x 2^20 fits an int32 warp sum), so such an utterance
+// always reports more frames than any max_len and jatts_fs2_plan fails loudly.
+static constexpr int kFrameSat = 1 << 30;
+__device__ __forceinline__ int regulator_frames(float dv, float alpha) {
+  const float f = (alpha != 1.0f) ? rintf(dv * alpha) : dv;
+  return static_cast<int>(fminf(f, 1048576.0f));
+}
 __global__ void durations_kernel(const float* __restrict__ logd, float alpha, RowLayout L,
                                  const int* __restrict__ tok_off, long long* __restrict__ dur_out,
                                  int* __restrict__ cum, int* __restrict__ n_frames) {
@@ -985,12 +993,12 @@ __global__ void durations_kernel(const float* __restrict__ logd, float alpha, Ro
     int dl = 0;
     if (t < T) {
       const float dv = fmaxf(rintf(expf(logd[s0 + t]) - 1.0f), 0.0f);
-      dur_out[tok_off[b] + t] = static_cast<long long>(dv);
-      dl = (alpha != 1.0f) ? static_cast<int>(rintf(dv * alpha)) : static_cast<int>(dv);
+      dur_out[tok_off[b] + t] = static_cast<long long>(fminf(dv, 9.0e18f));
+      dl = regulator_frames(dv, alpha);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o);
-    tot += dl;
+    tot = min(tot + dl, kFrameSat);
   }
   const bool all_zero = (tot == 0);  // length_regulator.py:86-94 with B == 1: every token becomes 1
   int carry = 0;
@@ -1003,7 +1011,7 @@ __global__ void durations_kernel(const float* __restrict__ logd, float alpha, Ro
         if (alpha == 1.0f) dur_out[tok_off[b] + t] = 1;  // in-place mutation visible to the caller (quirk 6)
       } else {
         const float dv = fmaxf(rintf(expf(logd[s0 + t]) - 1.0f), 0.0f);
-        dl = (alpha != 1.0f) ? static_cast<int>(rintf(dv * alpha)) : static_cast<int>(dv);
+        dl = regulator_frames(dv, alpha);
       }
     }
     int incl = dl;
@@ -1012,8 +1020,8 @@ __global__ void durations_kernel(const float* __restrict__ logd, float alpha, Ro
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    if (t < T) cum[s0 + t] = carry + incl;
-    carry += __shfl_sync(0xffffffffu, incl, 31);
+    if (t < T) cum[s0 + t] = min(carry + incl, kFrameSat);
+    carry = min(carry + __shfl_sync(0xffffffffu, incl, 31), kFrameSat);
   }
   if (lane == 0) n_frames[b] = carry;
 }
@@ -1256,11 +1264,8 @@ int output_conv_tanh(const bf16* x, int ld, int c, const float* w, float bias, i
   if (total == 0) return 0;
   if (c == 32 && ld == 32 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const int smem = 1024 + (OCT_TILE + k - 1) * OCT_PITCH;
-    static bool attr_set = false;
-    if (!attr_set) {
-      JB_CUDA_OK(cudaFuncSetAttribute(output_conv32_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + (OCT_TILE + OC_MAXK - 1) * OCT_PITCH));
-      attr_set = true;
-    }
+    JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(output_conv32_tiled_kernel),
+                                     1024 + (OCT_TILE + OC_MAXK - 1) * OCT_PITCH));
     output_conv32_tiled_kernel<<<static_cast<unsigned>((total + OCT_TILE - 1) / OCT_TILE), OCT_THREADS, smem, s>>>(
         x, w, bias, k, L, rate, frame_off, wave, pcm, total);
     JB_KERNEL_OK();

@@ -634,11 +634,7 @@ int launch_pair(const MrfPairProblem& p, cudaStream_t stream) {
   JB_PROPAGATE(make_tmap(&tw2, p.w2, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, C, C));
   JB_PROPAGATE(make_tmap(&tout, p.out, p.rows, C, p.out_ld, kp.out_m, C));
   auto kern = mrf_pair_kernel<C, TAPS>;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes = smem_bytes;
-  }
+  JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_bytes));
   if (kp.num_tiles == 0) return 0;
   const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
   cudaEvent_t e0 = nullptr, e1 = nullptr;

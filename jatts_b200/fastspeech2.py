@@ -175,6 +175,16 @@ class FastSpeech2(torch.nn.Module):
         need(spk_embed_dim is None or spk_embed_dim <= 0 or spk_embed_integration_type == "add",
              "spk_embed_integration_type != 'add'")
         need(0 < max_len <= _pack.PE_MAX_LEN, "max_len outside (0, 5000] (positional table is rebuilt above 5000)")
+        # the packed layout separates utterances by _pack.GAP_ROWS zero rows: a "same"-padded convolution must be
+        # odd (so that it is centred like the reference's padding=(k-1)//2) and its half width must fit the gap,
+        # else batch row i would read its neighbour (the conformer depthwise conv is bounded per utterance instead)
+        for what, k in (("positionwise_conv_kernel_size", positionwise_conv_kernel_size),
+                        ("duration_predictor_kernel_size", duration_predictor_kernel_size),
+                        ("pitch_predictor_kernel_size", pitch_predictor_kernel_size),
+                        ("energy_predictor_kernel_size", energy_predictor_kernel_size),
+                        ("postnet_filts", postnet_filts)):
+            need(k % 2 == 1 and (k - 1) // 2 <= _pack.GAP_ROWS, f"{what}={k} (must be odd and <= {2 * _pack.GAP_ROWS + 1})")
+        need(conformer_enc_kernel_size % 2 == 1 and conformer_dec_kernel_size % 2 == 1, "even conformer kernel size")
 
         self.idim, self.odim = idim, odim
         self.eos = idim - 1

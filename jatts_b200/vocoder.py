@@ -73,6 +73,9 @@ class HiFiGANGenerator(torch.nn.Module):
         need(use_additional_convs and bias, "use_additional_convs=False / bias=False")
         need(nonlinear_activation == "LeakyReLU", "activations other than LeakyReLU")
         need(not use_causal_conv, "causal convolutions")
+        # activations are stored as LeakyReLU(x) and x is recovered as r / slope for r < 0: slope must be in (0, 1]
+        need(0.0 < float(nonlinear_activation_params.get("negative_slope", 0.01)) <= 1.0,
+             "LeakyReLU negative_slope outside (0, 1]")
         need(kernel_size % 2 == 1 and all(k % 2 == 1 for k in resblock_kernel_sizes), "even kernel sizes")
         need(all(uk == 2 * s for uk, s in zip(upsample_kernel_sizes, upsample_scales)),
              "upsample_kernel_size != 2 * upsample_scale")

@@ -185,6 +185,21 @@ def postnet(x, sd, n_layers):
 
 
 @torch.no_grad()
+def fs2_log_durations(sd: Dict[str, torch.Tensor], cfg: dict, text: torch.Tensor,
+                      spemb: Optional[torch.Tensor] = None, dtype=torch.float32) -> torch.Tensor:
+    """The front half of ``_forward`` only (fastspeech2.py:583-612): encoder -> (speaker add) -> duration
+    predictor, returning the LOG durations before ``round(exp(x) - 1)``.  With ``dtype=torch.float64`` this
+    is the screening oracle of SURVEY.md 8(d) recipe B: a token whose fp64 ``exp(x) - 1`` lies next to a
+    rounding boundary may legitimately round either way in fp32 arithmetic."""
+    sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    hs = conformer_stack(sd["encoder.embed.0.weight"][text], sd, "encoder", cfg["elayers"], cfg["aheads"])
+    if cfg.get("spk_embed_dim"):
+        e = F.normalize(spemb.to(dtype).unsqueeze(0)).squeeze(0)
+        hs = hs + F.linear(e, sd["projection.weight"], sd["projection.bias"]).unsqueeze(0)
+    return predictor_stack(hs, sd, "duration_predictor", cfg["duration_predictor_layers"])
+
+
+@torch.no_grad()
 def fs2_inference(sd: Dict[str, torch.Tensor], cfg: dict, text: torch.Tensor,
                   spemb: Optional[torch.Tensor] = None, alpha: float = 1.0,
                   return_intermediates: bool = False) -> Dict[str, torch.Tensor]:

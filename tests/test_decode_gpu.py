@@ -10,6 +10,8 @@ import yaml
 
 import jatts_b200
 from jatts_b200 import decode
+from oracle import fs2 as ofs2
+from oracle import hifigan as ohg
 from oracle import recipes
 
 
@@ -83,3 +85,15 @@ def test_cli_writes_the_per_utterance_samples(tmp_path):
             assert w.getframerate() == sr == 24000 and w.getnchannels() == 1 and w.getsampwidth() == 2
             got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
         assert np.array_equal(got, pcm16_of(y.cpu()).numpy()), f"utt{i}: wav samples differ from the per-utterance path"
+
+    # ---- and against the CPU oracle (the reference's arithmetic): same number of samples (durations are bit-exact),
+    #      waveform within the stated AC-SNR bound; PCM_16 quantisation (-98 dB) is far below the bf16 noise floor
+    torch.set_num_threads(__import__("os").cpu_count() or 1)
+    for i in (0, 1, 3, 6):
+        ref = ofs2.fs2_inference(sd, cfg, texts[i])
+        yref = ohg.vocoder_decode(hsd, hcfg, ref["feat_gen"], vstats, tstats)
+        with wave.open(str(out / "wav" / f"utt{i}.wav"), "rb") as w:
+            got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32767.0
+        assert got.shape[0] == yref.shape[0] == int(ref["duration"].sum()) * 6
+        snr = ohg.ac_snr_db(yref, torch.from_numpy(got))
+        assert snr > 35.0, f"utt{i}: AC-SNR {snr:.1f} dB vs the oracle"
