@@ -163,6 +163,20 @@ typedef struct {
 } jatts_mrf_pair_args;
 JATTS_API int jatts_op_mrf_pair(const jatts_mrf_pair_args* a, void* stream);
 
+/* Legacy relative-position self-attention core (jatts/modules/transformer/attention.py:164-206 between the input
+ * projections and linear_out), the product kernel behind jatts_fs2_plan / jatts_fs2_run (jatts_b200/csrc/attention_tc.cu).
+ * x: [x_rows, 4*d_model] fp16 (hi, lo*2^11) pairs, per row [q + pos_bias_u | q + pos_bias_v | k | v]; utterance i owns
+ * rows seg_start[i] .. seg_start[i] + seg_len[i] - 1.  pos: [pos_rows, d_model] pair of linear_pos(pe).
+ * out: (hi, lo*2^11) pair of softmax(scores / sqrt(d_k)) . v, [x_rows, out_ld].  max_len >= every seg_len. */
+typedef struct {
+  const void* d_x_hi; const void* d_x_lo; int64_t x_rows;
+  const void* d_pos_hi; const void* d_pos_lo; int32_t pos_rows;
+  int32_t n_head, d_model;
+  const int32_t* d_seg_start; const int32_t* d_seg_len; int32_t nseg, max_len;
+  void* d_out_hi; void* d_out_lo; int32_t out_ld;
+} jatts_relpos_attention_args;
+JATTS_API int jatts_op_relpos_attention(const jatts_relpos_attention_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,11 +67,22 @@ class MrfPairArgs(C.Structure):
     ]
 
 
+class RelposAttentionArgs(C.Structure):
+    _fields_ = [
+        ("d_x_hi", C.c_void_p), ("d_x_lo", C.c_void_p), ("x_rows", C.c_int64),
+        ("d_pos_hi", C.c_void_p), ("d_pos_lo", C.c_void_p), ("pos_rows", C.c_int32),
+        ("n_head", C.c_int32), ("d_model", C.c_int32),
+        ("d_seg_start", C.c_void_p), ("d_seg_len", C.c_void_p), ("nseg", C.c_int32), ("max_len", C.c_int32),
+        ("d_out_hi", C.c_void_p), ("d_out_lo", C.c_void_p), ("out_ld", C.c_int32),
+    ]
+
+
 #: every symbol include/jatts_b200.h declares (tests/test_cabi.py checks the library exports them all)
 EXPORTS = (
     "jatts_abi_version", "jatts_last_error", "jatts_launch_count",
     "jatts_fs2_create", "jatts_fs2_destroy", "jatts_fs2_plan", "jatts_fs2_run",
     "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_hifigan_run_pcm16", "jatts_op_conv_gemm", "jatts_op_mrf_pair",
+    "jatts_op_relpos_attention",
     "jatts_profile_begin", "jatts_profile_end", "jatts_debug_set_trace",
 )
 
@@ -101,6 +112,7 @@ def _load():
                                             C.c_void_p]
     lib.jatts_op_conv_gemm.argtypes = [C.POINTER(ConvGemmArgs), C.c_int32, C.c_void_p]
     lib.jatts_op_mrf_pair.argtypes = [C.POINTER(MrfPairArgs), C.c_void_p]
+    lib.jatts_op_relpos_attention.argtypes = [C.POINTER(RelposAttentionArgs), C.c_void_p]
     lib.jatts_debug_set_trace.argtypes = [C.c_void_p]
     lib.jatts_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int64)]

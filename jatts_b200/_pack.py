@@ -108,14 +108,18 @@ def pack_fs2(sd: dict, cfg: dict, max_len: int) -> dict:
                 pack_taps(conv1d_taps(sd[q + b + ".w_1.weight"]), True, out, p + a + "_w1", sd[q + b + ".w_1.bias"])
                 pack_taps(conv1d_taps(sd[q + b + ".w_2.weight"]), True, out, p + a + "_w2", sd[q + b + ".w_2.bias"])
             sa = q + "self_attn."
-            wqkv = torch.cat([sd[sa + f"linear_{n}.weight"] for n in "qkv"], 0)
-            bqkv = torch.cat([sd[sa + f"linear_{n}.bias"] for n in "qkv"], 0)
+            # one projection GEMM emits [q + pos_bias_u | q + pos_bias_v | k | v] (attention.py:186-196 adds the two
+            # biases to q before the two score products): the second copy of W_q costs one N block of that GEMM
+            # and lets the attention kernel take every operand by TMA
+            wq, bq = sd[sa + "linear_q.weight"], sd[sa + "linear_q.bias"].float()
+            wqkv = torch.cat([wq, wq, sd[sa + "linear_k.weight"], sd[sa + "linear_v.weight"]], 0)
+            bqkv = torch.cat([bq + sd[sa + "pos_bias_u"].float().reshape(-1), bq + sd[sa + "pos_bias_v"].float().reshape(-1),
+                              sd[sa + "linear_k.bias"].float(), sd[sa + "linear_v.bias"].float()], 0)
             pack_taps(conv1d_taps(wqkv), True, out, p + "qkv", bqkv)
             pack_taps(conv1d_taps(sd[sa + "linear_out.weight"]), True, out, p + "out", sd[sa + "linear_out.bias"])
             # p = linear_pos(pos_emb) is batch independent (attention.py:182-184): precompute per layer
-            out[p + "pos"] = (pe @ sd[sa + "linear_pos.weight"].double().t()).float().contiguous()
-            out[p + "bias_u"] = sd[sa + "pos_bias_u"].float().reshape(-1).contiguous()
-            out[p + "bias_v"] = sd[sa + "pos_bias_v"].float().reshape(-1).contiguous()
+            pos_hi, pos_lo = split16((pe @ sd[sa + "linear_pos.weight"].double().t()).float())
+            out[p + "pos.hi"], out[p + "pos.lo"] = pos_hi.contiguous(), pos_lo.contiguous()
             cm = q + "conv_module."
             w1, b1 = glu_interleave(sd[cm + "pointwise_conv1.weight"][:, :, 0].float(), sd[cm + "pointwise_conv1.bias"].float())
             pack_taps(w1.unsqueeze(0), True, out, p + "pw1", b1)

@@ -49,6 +49,27 @@ extern "C" int jatts_op_mrf_pair(const jatts_mrf_pair_args* a, void* stream) {
   return mrf_pair(p, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int jatts_op_relpos_attention(const jatts_relpos_attention_args* a, void* stream) {
+  JB_REQUIRE(a != nullptr, JATTS_E_INVALID, "op_relpos_attention: null args");
+  RowLayout L{};
+  L.seg_start = a->d_seg_start; L.seg_len = a->d_seg_len; L.nseg = a->nseg; L.n_rows = static_cast<int>(a->x_rows);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t bytes = relpos_attention_scratch_bytes(a->max_len, a->nseg, a->n_head);
+  float* scratch = nullptr;   // the engine keeps its scratch; the test entry allocates one per call
+  if (bytes) JB_CUDA_OK(cudaMalloc(&scratch, bytes));
+  const int rc = relpos_attention(static_cast<const bf16*>(a->d_x_hi), static_cast<const bf16*>(a->d_x_lo), a->x_rows,
+                                  static_cast<const bf16*>(a->d_pos_hi), static_cast<const bf16*>(a->d_pos_lo), a->pos_rows,
+                                  a->n_head, a->d_model, L, a->max_len, scratch, bytes, static_cast<bf16*>(a->d_out_hi),
+                                  static_cast<bf16*>(a->d_out_lo), a->out_ld, s);
+  const cudaError_t e = cudaStreamSynchronize(s);
+  if (scratch) cudaFree(scratch);
+  if (rc == 0 && e != cudaSuccess) {
+    set_last_error(std::string("op_relpos_attention: ") + cudaGetErrorString(e));
+    return JATTS_E_CUDA;
+  }
+  return rc;
+}
+
 extern "C" int jatts_profile_begin(void) {
   for (auto& e : g_profile_events) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
   g_profile_events.clear();

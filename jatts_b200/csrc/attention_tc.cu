@@ -1,0 +1,481 @@
+// relpos_attention_tc_kernel: legacy relative-position self attention (jatts/modules/transformer/attention.py:164-206,
+// rel_shift :142-162) on tcgen05 tensor cores, TMEM accumulators and TMA operand loads, for any utterance length.
+//
+// Inputs are what the fused projection GEMM writes: one [rows, 4*D] matrix of fp16 (hi, lo*2^11) operand pairs per row
+//     [ q + bias_u | q + bias_v | k | v ]              (the two biased copies of q cost one extra N block of that GEMM)
+// and the per-layer table p = linear_pos(pe) [max_len, D] as the same kind of pair.  Per (utterance, head, tile of 127
+// query rows) one persistent CTA runs, with a = query row, b = key, n = position row:
+//
+//   phase 1   AC[a][b]  = (q_a + u) . k_b          128 x 128 score tiles, 3 MMAs per K step (hi.hi -> main accumulator,
+//   phase 2   BD[a][n]  = (q_a + v) . p_n          hi.lo' + lo'.hi -> a second one that the epilogue scales by 2^-11)
+//             both are written UNSHIFTED to a per-CTA fp32 scratch (L2 resident: 2 x 128 x T floats per CTA)
+//   softmax   the legacy rel-shift is a pure index map on the read side:
+//                 s[a][b] = AC[a][b] + ( b <= a ? BD[a][T-1-a+b] : b == a+1 ? 0 : BD[a+1][b-a-2] )
+//             one warp per row, lanes along b (coalesced); online max / sum in fp32; needs BD row a+1, hence 127 owned
+//             rows per 128-row tile
+//   phase 3   ctx = softmax(s / sqrt(d_k)) . V     probabilities are split into (hi, lo') pairs and written as the
+//             swizzled K-major A operand, 64 keys at a time; V tiles arrive by TMA exactly as they lie in memory
+//             ([key][d], i.e. the MN-major B operand); accumulators main / correction in TMEM
+//   epilogue  ctx -> (hi, lo') pair of the output projection's operand buffer
+//
+// No (B, H, T, T) tensor exists in HBM beyond the per-CTA scratch, no length limit below the positional table, and no
+// other attention kernel behind it: an unsupported head size is an error at engine creation.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-9 = workers
+// (score epilogue: the four whose warp-id % 4 covers the TMEM lane quadrants; softmax and the P operand: all eight).
+#include "../../include/jatts_b200.h"
+#include "conv_gemm.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace jb {
+namespace {
+
+constexpr int kAttThreads = 320;
+constexpr int kOwnRows = 127;                 // rows a tile stores (row 127 only supplies BD[a+1])
+constexpr int kTile16 = 128 * 128;            // one [128 rows x 64 cols] 16-bit tile, 128-byte swizzled: 16 KB
+constexpr int kStageB = 2 * kTile16;          // hi + lo
+constexpr int kRingB = 3;
+constexpr int kMaxNC = 3;                     // d_k <= 192
+constexpr int kRegionX = kMaxNC * kStageB;    // Q (one stage per 64-wide d_k chunk); later the two P chunk buffers
+constexpr int kRegionY = kRingB * kStageB;    // K / position ring; later the two V stages
+constexpr int kVBlock = 64 * 128;             // [64 keys x 64 dims] 8 KB
+constexpr int kVStage = 2 * kMaxNC * kVBlock; // hi blocks then lo blocks: 48 KB
+constexpr int kSmemBytes = kRegionX + kRegionY + 1024 /*barriers*/ + 1024 /*alignment*/;
+static_assert(2 * kVStage <= kRegionY && 2 * kStageB <= kRegionX, "phase-3 buffers alias the phase-1/2 regions");
+
+struct AttParams {
+  const int* seg_start;
+  const int* seg_len;
+  int n_head, dk, nc, d_model;
+  int tiles_per_utt, total_tiles;
+  int tp;            // scratch row pitch in floats (multiple of 128)
+  float* scratch;    // [gridDim.x][2][128][tp]
+  bf16* out_hi;
+  bf16* out_lo;
+  int out_ld;
+  float scale;       // 1 / sqrt(d_k)
+};
+
+struct TileInfo {
+  int h, a0, T, seg0;
+  bool valid;
+};
+__device__ __forceinline__ TileInfo decode_tile(const AttParams& P, int tile) {
+  TileInfo t;
+  const int rt = tile % P.tiles_per_utt;
+  const int bh = tile / P.tiles_per_utt;
+  const int b = bh / P.n_head;
+  t.h = bh - b * P.n_head;
+  t.a0 = rt * kOwnRows;
+  t.T = __ldg(P.seg_len + b);
+  t.seg0 = __ldg(P.seg_start + b);
+  t.valid = t.a0 < t.T;
+  return t;
+}
+
+// fp16 operands (format 0), fp32 accumulate; B either K-major or MN-major (bit 16)
+__host__ __device__ constexpr uint32_t att_idesc(int n, bool b_mn_major) {
+  return (1u << 4) | (b_mn_major ? (1u << 16) : 0u) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_f16_bits(bf16 a, bf16 b) {   // two 16-bit patterns -> one word
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+__global__ void __launch_bounds__(kAttThreads, 1)
+relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                           const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
+                           const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constant__ CUtensorMap tm_p_lo,
+                           const __grid_constant__ AttParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* X = smem;
+  uint8_t* Y = smem + kRegionX;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Y + kRegionY);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_free = bars + 1;
+  uint64_t* s2_done = bars + 2;
+  uint64_t* ctx_full = bars + 3;
+  uint64_t* tile_free = bars + 4;
+  uint64_t* b_full = bars + 5;     // [3]
+  uint64_t* b_empty = bars + 8;    // [3]
+  uint64_t* s_full = bars + 11;    // [2]
+  uint64_t* s_empty = bars + 13;   // [2]
+  uint64_t* p_full = bars + 15;    // [2]
+  uint64_t* p_empty = bars + 17;   // [2]
+  uint64_t* v_full = bars + 19;    // [2]
+  uint64_t* v_empty = bars + 21;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo);
+    tma_prefetch_desc(&tm_v_hi); tma_prefetch_desc(&tm_v_lo);
+    tma_prefetch_desc(&tm_p_hi); tma_prefetch_desc(&tm_p_lo);
+    mbar_init(q_full, 1); mbar_init(q_free, 1); mbar_init(s2_done, 1); mbar_init(ctx_full, 1);
+    mbar_init(tile_free, 4);
+    for (int i = 0; i < kRingB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // the projection GEMM's outputs are visible from here
+
+  const int D = P.d_model;
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (elect_one()) {
+      uint32_t nb = 0, nv = 0, it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileInfo ti = decode_tile(P, tile);
+        if (!ti.valid) continue;
+        const int nkt = (ti.T + 127) >> 7, nkc = (ti.T + 63) >> 6;
+        const int hcol = ti.h * P.dk;
+        if (it > 0) mbar_wait(ctx_full, (it - 1) & 1);   // every MMA of the previous tile has read its operands
+        auto load_q = [&](int which) {
+          mbar_expect_tx(q_full, static_cast<uint32_t>(P.nc) * kStageB);
+          for (int c = 0; c < P.nc; ++c) {
+            tma_load_2d(&tm_x_hi, q_full, X + c * kStageB, which * D + hcol + c * 64, ti.seg0 + ti.a0);
+            tma_load_2d(&tm_x_lo, q_full, X + c * kStageB + kTile16, which * D + hcol + c * 64, ti.seg0 + ti.a0);
+          }
+        };
+        auto load_b = [&](const CUtensorMap* mh, const CUtensorMap* ml, int col0, int row) {
+          for (int c = 0; c < P.nc; ++c) {
+            const uint32_t st = nb % kRingB;
+            mbar_wait(&b_empty[st], ((nb / kRingB) & 1) ^ 1);
+            mbar_expect_tx(&b_full[st], kStageB);
+            tma_load_2d(mh, &b_full[st], Y + st * kStageB, col0 + c * 64, row);
+            tma_load_2d(ml, &b_full[st], Y + st * kStageB + kTile16, col0 + c * 64, row);
+            ++nb;
+          }
+        };
+        load_q(0);                                                                         // q + bias_u
+        for (int j = 0; j < nkt; ++j) load_b(&tm_x_hi, &tm_x_lo, 2 * D + hcol, ti.seg0 + j * 128);   // keys
+        mbar_wait(q_free, it & 1);                                                         // phase-1 MMAs done with Q
+        load_q(1);                                                                         // q + bias_v
+        for (int j = 0; j < nkt; ++j) load_b(&tm_p_hi, &tm_p_lo, hcol, j * 128);           // positions 0 .. T-1
+        mbar_wait(s2_done, it & 1);                                                        // ring and Q regions are free
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t st = nv & 1;
+          mbar_wait(&v_empty[st], ((nv >> 1) & 1) ^ 1);
+          mbar_expect_tx(&v_full[st], static_cast<uint32_t>(2 * P.nc) * kVBlock);
+          for (int c = 0; c < P.nc; ++c) {
+            tma_load_2d(&tm_v_hi, &v_full[st], Y + st * kVStage + c * kVBlock, 3 * D + hcol + c * 64, ti.seg0 + kc * 64);
+            tma_load_2d(&tm_v_lo, &v_full[st], Y + st * kVStage + (P.nc + c) * kVBlock, 3 * D + hcol + c * 64, ti.seg0 + kc * 64);
+          }
+          ++nv;
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = att_idesc(128, false);
+      const uint32_t idesc_c = att_idesc(P.dk, true);
+      constexpr uint32_t desc_hi = static_cast<uint32_t>(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, v1, SWIZZLE_128B
+      constexpr uint32_t k_lo0 = 1u << 16;                                      // K-major: LBO unused
+      constexpr uint32_t v_lo0 = static_cast<uint32_t>(kVBlock >> 4) << 16;     // MN-major: LBO = next 64-wide block of d
+      const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y);
+      uint32_t nb = 0, nv = 0, sb = 0, pc = 0, qf = 0, it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileInfo ti = decode_tile(P, tile);
+        if (!ti.valid) continue;
+        const int nkt = (ti.T + 127) >> 7, nkc = (ti.T + 63) >> 6;
+        if (it > 0) mbar_wait(tile_free, (it - 1) & 1);   // the context accumulators of the previous tile were read
+        tc_fence_after();
+        for (int ph = 0; ph < 2; ++ph) {
+          mbar_wait(q_full, qf & 1);
+          ++qf;
+          tc_fence_after();
+          for (int j = 0; j < nkt; ++j) {
+            const uint32_t buf = sb & 1;
+            mbar_wait(&s_empty[buf], ((sb >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_main = tmem_base + buf * 256u, d_corr = d_main + 128u;
+            for (int c = 0; c < P.nc; ++c) {
+              const uint32_t st = nb % kRingB;
+              mbar_wait(&b_full[st], (nb / kRingB) & 1);
+              tc_fence_after();
+              const uint32_t a0 = x_addr + c * kStageB, b0 = y_addr + st * kStageB;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ah = k_lo0 + ((a0 + k * 32) >> 4), al = k_lo0 + ((a0 + kTile16 + k * 32) >> 4);
+                const uint32_t bh = k_lo0 + ((b0 + k * 32) >> 4), bl = k_lo0 + ((b0 + kTile16 + k * 32) >> 4);
+                const uint32_t acc = (c | k) != 0 ? 1u : 0u;
+                tc_mma_bf16_lohi(d_main, ah, desc_hi, bh, desc_hi, idesc_s, acc);
+                tc_mma_bf16_lohi(d_corr, ah, desc_hi, bl, desc_hi, idesc_s, acc);
+                tc_mma_bf16_lohi(d_corr, al, desc_hi, bh, desc_hi, idesc_s, 1u);
+              }
+              tc_commit(&b_empty[st]);
+              ++nb;
+            }
+            tc_commit(&s_full[buf]);
+            ++sb;
+          }
+          tc_commit(ph == 0 ? q_free : s2_done);
+        }
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t pb = pc & 1, vs = nv & 1;
+          mbar_wait(&p_full[pb], (pc >> 1) & 1);
+          mbar_wait(&v_full[vs], (nv >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a0 = x_addr + pb * kStageB, b0 = y_addr + vs * kVStage;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // 16 keys per MMA: 32 B along the A rows, two 8-key groups (2 KB) of V
+            const uint32_t ah = k_lo0 + ((a0 + k * 32) >> 4), al = k_lo0 + ((a0 + kTile16 + k * 32) >> 4);
+            const uint32_t bh = v_lo0 + ((b0 + k * 2048) >> 4), bl = v_lo0 + ((b0 + P.nc * kVBlock + k * 2048) >> 4);
+            const uint32_t acc = (kc | k) != 0 ? 1u : 0u;
+            tc_mma_bf16_lohi(tmem_base, ah, desc_hi, bh, desc_hi, idesc_c, acc);
+            tc_mma_bf16_lohi(tmem_base + 256u, ah, desc_hi, bl, desc_hi, idesc_c, acc);
+            tc_mma_bf16_lohi(tmem_base + 256u, al, desc_hi, bh, desc_hi, idesc_c, 1u);
+          }
+          tc_commit(&p_empty[pb]);
+          tc_commit(&v_empty[vs]);
+          ++pc;
+          ++nv;
+        }
+        tc_commit(ctx_full);
+        ++it;
+      }
+    }
+  } else {
+    // ============================ workers ============================
+    const int w = warp - 2;            // 0..7: rows w*16 .. w*16+15 in the softmax / P phases
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may read
+    const bool epi = w < 4;            // warps 2..5 cover quadrants 2, 3, 0, 1
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int tp = P.tp;
+    float* scr = P.scratch + static_cast<size_t>(blockIdx.x) * 2 * 128 * tp;
+    float* AC = scr;
+    const float* BD = scr + static_cast<size_t>(128) * tp;
+    const uint32_t x_addr = smem_u32(X);
+    constexpr float kInvSplit = 1.0f / kSplitScale;
+    uint32_t se = 0, pc = 0, it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileInfo ti = decode_tile(P, tile);
+      if (!ti.valid) continue;
+      const int T = ti.T, a0 = ti.a0;
+      const int nkt = (T + 127) >> 7, nkc = (T + 63) >> 6;
+      // ---- score epilogue: TMEM (main + corr * 2^-11) -> scratch, thread = row
+      if (epi) {
+        const int r = quad * 32 + lane;
+        for (int ph = 0; ph < 2; ++ph) {
+          float* dst = scr + (static_cast<size_t>(ph) * 128 + r) * tp;
+          for (int j = 0; j < nkt; ++j) {
+            const uint32_t buf = se & 1;
+            mbar_wait(&s_full[buf], (se >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t m[32], c[32];
+              tmem_ld32(lane_base + buf * 256u + static_cast<uint32_t>(ch * 32), m);
+              tmem_ld32(lane_base + buf * 256u + 128u + static_cast<uint32_t>(ch * 32), c);
+              tmem_ld_wait();
+              if (ch == 3) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[buf]);
+              }
+              float4* o = reinterpret_cast<float4*>(dst + j * 128 + ch * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                o[i] = make_float4(__uint_as_float(m[4 * i]) + __uint_as_float(c[4 * i]) * kInvSplit,
+                                   __uint_as_float(m[4 * i + 1]) + __uint_as_float(c[4 * i + 1]) * kInvSplit,
+                                   __uint_as_float(m[4 * i + 2]) + __uint_as_float(c[4 * i + 2]) * kInvSplit,
+                                   __uint_as_float(m[4 * i + 3]) + __uint_as_float(c[4 * i + 3]) * kInvSplit);
+            }
+            ++se;
+          }
+        }
+      }
+      __threadfence_block();
+      named_bar_sync(1, 256);
+      // ---- softmax statistics, 16 rows per warp, lanes along the keys; the combined, scaled score replaces AC
+      float mrow[16], lrow[16];
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) { mrow[rr] = -INFINITY; lrow[rr] = 0.f; }
+      for (int b0 = 0; b0 < T; b0 += 32) {
+        const int b = b0 + lane;
+        float sv[16];
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          const int r = w * 16 + rr, a = a0 + r;
+          float s = -INFINITY;
+          if (b < T && r < kOwnRows && a < T) {
+            float bd = 0.f;
+            if (b <= a) bd = BD[static_cast<size_t>(r) * tp + (T - 1 - a + b)];
+            else if (b >= a + 2) bd = BD[static_cast<size_t>(r + 1) * tp + (b - a - 2)];
+            s = (AC[static_cast<size_t>(r) * tp + b] + bd) * P.scale;
+            AC[static_cast<size_t>(r) * tp + b] = s;
+          }
+          sv[rr] = s;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          if (sv[rr] > -INFINITY) {
+            const float mn = fmaxf(mrow[rr], sv[rr]);
+            lrow[rr] = lrow[rr] * expf(mrow[rr] - mn) + expf(sv[rr] - mn);
+            mrow[rr] = mn;
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const float M = warp_max(mrow[rr]);
+        const float part = mrow[rr] > -INFINITY ? lrow[rr] * expf(mrow[rr] - M) : 0.f;
+        const float L = warp_sum(part);
+        mrow[rr] = M;
+        lrow[rr] = L > 0.f ? 1.0f / L : 0.f;   // rows this tile does not own have no scores: probability 0
+      }
+      __syncwarp();   // the in-place scores of a row are read below by other lanes of this warp
+      // ---- phase 3: probabilities of 64 keys -> (hi, lo') A-operand chunk (lane = 2 adjacent keys)
+      for (int kc = 0; kc < nkc; ++kc) {
+        const uint32_t pb = pc & 1;
+        mbar_wait(&p_empty[pb], ((pc >> 1) & 1) ^ 1);
+        const int key = kc * 64 + 2 * lane;
+        const uint32_t dst0 = x_addr + pb * kStageB + static_cast<uint32_t>((lane & 3) * 4);
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          const int r = w * 16 + rr;
+          float p0 = 0.f, p1 = 0.f;
+          if (lrow[rr] > 0.f && key < T) {
+            const float2 s2 = *reinterpret_cast<const float2*>(AC + static_cast<size_t>(r) * tp + key);
+            p0 = expf(s2.x - mrow[rr]) * lrow[rr];
+            if (key + 1 < T) p1 = expf(s2.y - mrow[rr]) * lrow[rr];
+          }
+          bf16 h0, l0, h1, l1;
+          split_op16(p0, h0, l0);
+          split_op16(p1, h1, l1);
+          const uint32_t a = dst0 + static_cast<uint32_t>(r * 128) + (static_cast<uint32_t>((lane >> 2) ^ (r & 7)) << 4);
+          sts32(a, pack_f16_bits(h0, h1));
+          sts32(a + kTile16, pack_f16_bits(l0, l1));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[pb]);
+        ++pc;
+      }
+      // ---- context epilogue: TMEM -> (hi, lo') rows of the output projection's operand
+      if (epi) {
+        mbar_wait(ctx_full, it & 1);
+        tc_fence_after();
+        const int r = quad * 32 + lane, a = a0 + r;
+        const bool valid = r < kOwnRows && a < T;
+        const size_t orow = static_cast<size_t>(ti.seg0 + a) * P.out_ld + ti.h * P.dk;
+        const int nch = P.dk >> 5;
+        for (int ch = 0; ch < nch; ++ch) {
+          uint32_t m[32], c[32];
+          tmem_ld32(lane_base + static_cast<uint32_t>(ch * 32), m);
+          tmem_ld32(lane_base + 256u + static_cast<uint32_t>(ch * 32), c);
+          tmem_ld_wait();
+          if (ch == nch - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tile_free);
+          }
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                bf16 h0, l0, h1, l1;
+                split_op16(__uint_as_float(m[g * 8 + 2 * i]) + __uint_as_float(c[g * 8 + 2 * i]) * kInvSplit, h0, l0);
+                split_op16(__uint_as_float(m[g * 8 + 2 * i + 1]) + __uint_as_float(c[g * 8 + 2 * i + 1]) * kInvSplit, h1, l1);
+                hw[i] = pack_f16_bits(h0, h1);
+                lw[i] = pack_f16_bits(l0, l1);
+              }
+              *reinterpret_cast<uint4*>(P.out_hi + orow + ch * 32 + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(P.out_lo + orow + ch * 32 + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+        }
+      }
+      ++it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+bool relpos_attention_supported(int n_head, int d_model) {
+  if (n_head <= 0 || d_model % n_head != 0) return false;
+  const int dk = d_model / n_head;
+  return dk % 64 == 0 && dk <= 64 * kMaxNC;
+}
+
+size_t relpos_attention_scratch_bytes(int max_len, int nseg, int n_head) {
+  if (max_len <= 0 || nseg <= 0) return 0;
+  const long long tiles = static_cast<long long>(nseg) * n_head * ceil_div(max_len, kOwnRows);
+  const long long grid = tiles < num_sms() ? tiles : num_sms();
+  return static_cast<size_t>(grid) * 2 * 128 * round_up(max_len, 128) * sizeof(float);
+}
+
+int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const bf16* pos_hi, const bf16* pos_lo,
+                     int pos_rows, int n_head, int d_model, RowLayout L, int max_len, float* scratch,
+                     size_t scratch_bytes, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s) {
+  JB_REQUIRE(relpos_attention_supported(n_head, d_model), JATTS_E_UNSUPPORTED,
+             "attention: d_k must be 64, 128 or 192 (tcgen05 kernel; there is no other attention path)");
+  JB_REQUIRE(x_hi && x_lo && pos_hi && pos_lo && out_hi && out_lo, JATTS_E_INVALID, "attention: null operand");
+  JB_REQUIRE(max_len <= pos_rows, JATTS_E_UNSUPPORTED, "attention: utterance longer than the positional table");
+  JB_REQUIRE(out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_lo) & 15) == 0,
+             JATTS_E_INVALID, "attention: output rows must be 16-byte aligned");
+  if (L.nseg == 0 || max_len == 0) return 0;
+  JB_REQUIRE(scratch != nullptr && scratch_bytes >= relpos_attention_scratch_bytes(max_len, L.nseg, n_head), JATTS_E_INVALID,
+             "attention: scratch buffer too small");
+  AttParams P{};
+  P.seg_start = L.seg_start;
+  P.seg_len = L.seg_len;
+  P.n_head = n_head;
+  P.dk = d_model / n_head;
+  P.nc = P.dk / 64;
+  P.d_model = d_model;
+  P.tiles_per_utt = ceil_div(max_len, kOwnRows);
+  P.total_tiles = L.nseg * n_head * P.tiles_per_utt;
+  P.tp = round_up(max_len, 128);
+  P.scratch = scratch;
+  P.out_hi = out_hi;
+  P.out_lo = out_lo;
+  P.out_ld = out_ld;
+  P.scale = 1.0f / sqrtf(static_cast<float>(P.dk));
+  CUtensorMap mxh, mxl, mvh, mvl, mph, mpl;
+  JB_PROPAGATE(make_tmap(&mxh, x_hi, x_rows, 4 * d_model, 4 * d_model, 128));
+  JB_PROPAGATE(make_tmap(&mxl, x_lo, x_rows, 4 * d_model, 4 * d_model, 128));
+  JB_PROPAGATE(make_tmap(&mvh, x_hi, x_rows, 4 * d_model, 4 * d_model, 64));
+  JB_PROPAGATE(make_tmap(&mvl, x_lo, x_rows, 4 * d_model, 4 * d_model, 64));
+  JB_PROPAGATE(make_tmap(&mph, pos_hi, pos_rows, d_model, d_model, 128));
+  JB_PROPAGATE(make_tmap(&mpl, pos_lo, pos_rows, d_model, d_model, 128));
+  JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(relpos_attention_tc_kernel), kSmemBytes));
+  const int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  JB_CUDA_OK(launch_tc(relpos_attention_tc_kernel, grid, kAttThreads, kSmemBytes, s, 1, mxh, mxl, mvh, mvl, mph, mpl, P));
+  JB_KERNEL_OK();
+  return 0;
+}
+
+}  // namespace jb

@@ -16,7 +16,8 @@ struct ConformerLayerW {
   const float *ln_ffm_g, *ln_ffm_b, *ln_mha_g, *ln_mha_b, *ln_conv_g, *ln_conv_b, *ln_ff_g, *ln_ff_b, *ln_fin_g,
       *ln_fin_b;
   ConvW ffm_w1, ffm_w2, ff_w1, ff_w2, qkv, out, pw1, pw2;
-  const float *pos, *bias_u, *bias_v;  // pos: [max_len, D] = linear_pos(pe)
+  const bf16 *pos_hi, *pos_lo;         // [max_len, D] fp16 (hi, lo*2^11) pair of linear_pos(pe); the biases u / v
+                                       // are folded into the projection GEMM (its two biased copies of q)
   const float *dw_wT, *dw_b;           // BatchNorm folded
   int dw_k;
 };
@@ -49,7 +50,10 @@ struct jatts_fs2 {
   Arena arena;
   int cap_rows = 0, cap_utt = 0;
   // workspace views (valid after ensure_workspace)
-  float *x, *hs, *qkv, *g, *pf, *before, *after, *s_dur, *s_pitch, *s_energy, *o_pitch, *o_energy;
+  float *x, *hs, *g, *pf, *before, *after, *s_dur, *s_pitch, *s_energy, *o_pitch, *o_energy;
+  bf16 *q4_hi, *q4_lo;   // [rows, 4*D] projection output: q + u | q + v | k | v as operand pairs
+  float* att_scratch = nullptr;   // per-CTA score rows of the attention kernel (own allocation, grown on demand)
+  size_t att_scratch_bytes = 0;
   bf16 *h_hi, *h_lo, *t_hi, *t_lo, *c_hi, *c_lo, *p_hi, *p_lo, *b_hi, *b_lo, *pa_hi, *pa_lo, *pb_hi, *pb_lo;
   long long* o_dur;
   int *cum, *lr_index, *d_nframes;
@@ -91,13 +95,12 @@ static int load_conformer(const WeightTable& wt, const std::string& pre, int n_l
     JB_PROPAGATE(load_conv(wt, p + "ffm_w2", ffn_k, d, units, true, true, d, &L.ffm_w2));
     JB_PROPAGATE(load_conv(wt, p + "ff_w1", ffn_k, units, d, true, true, units, &L.ff_w1));
     JB_PROPAGATE(load_conv(wt, p + "ff_w2", ffn_k, d, units, true, true, d, &L.ff_w2));
-    JB_PROPAGATE(load_conv(wt, p + "qkv", 1, 3 * d, d, true, true, 3 * d, &L.qkv));
+    JB_PROPAGATE(load_conv(wt, p + "qkv", 1, 4 * d, d, true, true, 4 * d, &L.qkv));   // [q+u | q+v | k | v]
     JB_PROPAGATE(load_conv(wt, p + "out", 1, d, d, true, true, d, &L.out));
     JB_PROPAGATE(load_conv(wt, p + "pw1", 1, 2 * d, d, true, true, d, &L.pw1));  // GLU: d outputs from 2d columns
     JB_PROPAGATE(load_conv(wt, p + "pw2", 1, d, d, true, true, d, &L.pw2));
-    JB_PROPAGATE(wt.f32(p + "pos", static_cast<long long>(max_len) * d, &L.pos));
-    JB_PROPAGATE(wt.f32(p + "bias_u", d, &L.bias_u));
-    JB_PROPAGATE(wt.f32(p + "bias_v", d, &L.bias_v));
+    JB_PROPAGATE(wt.get(p + "pos.hi", JATTS_F16, static_cast<long long>(max_len) * d, reinterpret_cast<const void**>(&L.pos_hi)));
+    JB_PROPAGATE(wt.get(p + "pos.lo", JATTS_F16, static_cast<long long>(max_len) * d, reinterpret_cast<const void**>(&L.pos_lo)));
     JB_PROPAGATE(wt.f32(p + "dw.wT", static_cast<long long>(dw_k) * d, &L.dw_wT));
     JB_PROPAGATE(wt.f32(p + "dw.b", d, &L.dw_b));
     L.dw_k = dw_k;
@@ -181,7 +184,7 @@ static int ensure_workspace(jatts_fs2* h, int rows, int n_utt, int n_text) {
   size_t bytes = 0;
   auto f32 = [&](size_t cols) { bytes += Arena::padded(sizeof(float) * R * cols); };
   auto b16 = [&](size_t cols) { bytes += 2 * Arena::padded(sizeof(bf16) * R * cols); };
-  f32(d); f32(d); f32(3 * d); f32(d); f32(pc); f32(c.odim); f32(c.odim);      // x hs qkv g pf before after
+  f32(d); f32(d); b16(4 * d); f32(d); f32(pc); f32(c.odim); f32(c.odim);      // x hs q4 g pf before after
   for (int i = 0; i < 5; ++i) f32(1);                                          // s_dur s_pitch s_energy o_pitch o_energy
   b16(d); b16(u); b16(d); b16(pc); b16(od_pad); b16(pn); b16(pn);              // h t c p b pa pb
   bytes += Arena::padded(sizeof(long long) * R) + 2 * Arena::padded(sizeof(int) * R);  // o_dur cum lr_index
@@ -191,7 +194,8 @@ static int ensure_workspace(jatts_fs2* h, int rows, int n_utt, int n_text) {
   a.reset();
   h->x = a.take<float>(size_t(R) * d);
   h->hs = a.take<float>(size_t(R) * d);
-  h->qkv = a.take<float>(size_t(R) * 3 * d);
+  h->q4_hi = a.take<bf16>(size_t(R) * 4 * d);
+  h->q4_lo = a.take<bf16>(size_t(R) * 4 * d);
   h->g = a.take<float>(size_t(R) * d);
   h->pf = a.take<float>(size_t(R) * pc);
   h->before = a.take<float>(size_t(R) * c.odim);
@@ -258,6 +262,14 @@ static int conv_ffn(jatts_fs2* h, const ConvW& w1, const ConvW& w2, const RowLay
 static int conformer_stack(jatts_fs2* h, const ConformerW& W, const RowLayout& L, int max_len, cudaStream_t s) {
   const jatts_fs2_config& c = h->cfg;
   const int d = c.adim;
+  const size_t need = relpos_attention_scratch_bytes(max_len, L.nseg, c.aheads);
+  if (need > h->att_scratch_bytes) {
+    if (h->att_scratch) JB_CUDA_OK(cudaFree(h->att_scratch));   // cudaFree waits for the kernels still using it
+    h->att_scratch = nullptr;
+    h->att_scratch_bytes = 0;
+    JB_CUDA_OK(cudaMalloc(&h->att_scratch, need));
+    h->att_scratch_bytes = need;
+  }
   const float eps = 1e-12f;  // layer_norm.py:23
   for (const ConformerLayerW& Lw : W.layers) {
     // macaron FFN (encoder_layer.py:112-122)
@@ -266,9 +278,10 @@ static int conformer_stack(jatts_fs2* h, const ConformerW& W, const RowLayout& L
     // self attention (encoder_layer.py:124-147, attention.py:164-206)
     JB_PROPAGATE(layernorm_rows(h->x, d, Lw.ln_mha_g, Lw.ln_mha_b, eps, L, nullptr, h->h_hi, h->h_lo, d, s));
     ConvGemmEpilogue eq{};
-    eq.out_f32 = h->qkv; eq.out_f32_ld = 3 * d;
+    eq.out_hi = h->q4_hi; eq.out_lo = h->q4_lo; eq.out_bf_ld = 4 * d;
     JB_PROPAGATE(run_conv(Lw.qkv, h->h_hi, h->h_lo, d, L, eq, s));
-    JB_PROPAGATE(relpos_attention(h->qkv, Lw.pos, Lw.bias_u, Lw.bias_v, c.aheads, d, L, max_len, h->c_hi, h->c_lo, d, s));
+    JB_PROPAGATE(relpos_attention(h->q4_hi, h->q4_lo, h->cap_rows, Lw.pos_hi, Lw.pos_lo, c.max_len, c.aheads, d, L, max_len,
+                                  h->att_scratch, h->att_scratch_bytes, h->c_hi, h->c_lo, d, s));
     ConvGemmEpilogue eo{};
     eo.res_f32 = h->x; eo.res_ld = d; eo.out_f32 = h->x; eo.out_f32_ld = d;
     JB_PROPAGATE(run_conv(Lw.out, h->c_hi, h->c_lo, d, L, eo, s));
@@ -314,6 +327,8 @@ extern "C" int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor*
   JB_REQUIRE(cfg && weights && out, JATTS_E_INVALID, "fs2_create: null argument");
   JB_REQUIRE(cfg->adim % 64 == 0 && cfg->adim <= 512, JATTS_E_UNSUPPORTED, "adim must be a multiple of 64, <= 512");
   JB_REQUIRE(cfg->adim % cfg->aheads == 0, JATTS_E_INVALID, "adim % aheads");
+  JB_REQUIRE(relpos_attention_supported(cfg->aheads, cfg->adim), JATTS_E_UNSUPPORTED,
+             "adim / aheads must be 64, 128 or 192 (head size of the tcgen05 attention kernel)");
   JB_REQUIRE(cfg->eunits % 64 == 0 && cfg->dunits % 64 == 0, JATTS_E_UNSUPPORTED, "ffn units must be a multiple of 64");
   JB_REQUIRE(cfg->dur_chans % 64 == 0 && cfg->pitch_chans % 64 == 0 && cfg->energy_chans % 64 == 0 &&
                  cfg->dur_chans <= 512 && cfg->pitch_chans <= 512 && cfg->energy_chans <= 512,
@@ -368,6 +383,7 @@ extern "C" void jatts_fs2_destroy(jatts_fs2* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   h->arena.release();
+  if (h->att_scratch) cudaFree(h->att_scratch);
   if (h->h_small) cudaFreeHost(h->h_small);
   if (h->h_nframes) cudaFreeHost(h->h_nframes);
   if (h->d_small) cudaFree(h->d_small);

@@ -184,705 +184,6 @@ int split_rows(const float* x, int c, RowLayout L, bf16* hi, bf16* lo, int bf_ld
 }
 
 // ------------------------------------------------------------------------------------------------
-// legacy relative-position attention (attention.py:164-206), fp32 on CUDA cores.
-//
-// One CTA = (query tile of R rows, utterance, head).  With BD[a,n] = (q_a + v) . p_n the reference's
-// rel_shift (attention.py:142-162) has the closed form
-//     shifted[a,b] = BD[a, T-1-a+b]   (b <= a),   0 (b == a+1),   BD[a+1, b-a-2]   (b > a+1)
-// so score row a needs q_a against keys and against p, and q_{a+1} against p.
-// ------------------------------------------------------------------------------------------------
-static constexpr int ATT_TK = 64;       // keys / positions per smem tile
-static constexpr int ATT_THREADS = 256;
-
-template <int R>
-__global__ void __launch_bounds__(ATT_THREADS)
-relpos_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ pos, const float* __restrict__ bias_u,
-                        const float* __restrict__ bias_v, int d_model, int dk, RowLayout L, int t_pad,
-                        bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int out_ld) {
-  constexpr int RPT = R / 4;  // query rows per thread
-  const int b = blockIdx.y, h = blockIdx.z;
-  const int T = L.seg_len[b];
-  const int a0 = blockIdx.x * R;
-  if (a0 >= T) return;
-  const long long base = L.seg_start[b];
-  const int ks = dk + 4;  // padded smem row stride (floats): conflict-free LDS.128
-  extern __shared__ float sm[];
-  float* qu = sm;                    // [R][dk]
-  float* qv = qu + R * dk;           // [R+1][dk]
-  float* S = qv + (R + 1) * dk;      // [R][t_pad]
-  float* tile = S + R * t_pad;       // [ATT_TK][ks]
-  const int tid = threadIdx.x;
-  const int tx = tid & 63, ty = tid >> 6;
-  const int ld3 = 3 * d_model;
-  const int dk4 = dk >> 2;
-
-  for (int i = tid; i < (R + 1) * dk; i += ATT_THREADS) {
-    const int r = i / dk, d = i - r * dk;
-    const int a = a0 + r;
-    float q = 0.f;
-    if (a < T) q = qkv[(base + a) * ld3 + h * dk + d];
-    if (r < R) qu[r * dk + d] = (a < T) ? q + bias_u[h * dk + d] : 0.f;
-    qv[r * dk + d] = (a < T) ? q + bias_v[h * dk + d] : 0.f;
-  }
-  __syncthreads();
-
-  // ---- phase A: S[r][key] = (q_a + u) . k_key
-  for (int k0 = 0; k0 < T; k0 += ATT_TK) {
-    for (int i = tid; i < ATT_TK * dk4; i += ATT_THREADS) {
-      const int kk = i / dk4, d4 = i - kk * dk4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + kk < T) v = *reinterpret_cast<const float4*>(qkv + (base + k0 + kk) * ld3 + d_model + h * dk + d4 * 4);
-      *reinterpret_cast<float4*>(tile + kk * ks + d4 * 4) = v;
-    }
-    __syncthreads();
-    float acc[RPT];
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) acc[i] = 0.f;
-    const float* kr = tile + tx * ks;
-    for (int d = 0; d < dk; d += 4) {
-      const float4 kv = *reinterpret_cast<const float4*>(kr + d);
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const float4 q = *reinterpret_cast<const float4*>(qu + (ty * RPT + i) * dk + d);
-        acc[i] += (q.x * kv.x + q.y * kv.y) + (q.z * kv.z + q.w * kv.w);
-      }
-    }
-    if (k0 + tx < T) {
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) S[(ty * RPT + i) * t_pad + k0 + tx] = acc[i];
-    }
-    __syncthreads();
-  }
-
-  // ---- phase B: add the shifted positional term
-  for (int n0 = 0; n0 < T; n0 += ATT_TK) {
-    for (int i = tid; i < ATT_TK * dk4; i += ATT_THREADS) {
-      const int kk = i / dk4, d4 = i - kk * dk4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + kk < T) v = *reinterpret_cast<const float4*>(pos + static_cast<long long>(n0 + kk) * d_model + h * dk + d4 * 4);
-      *reinterpret_cast<float4*>(tile + kk * ks + d4 * 4) = v;
-    }
-    __syncthreads();
-    float acc[RPT + 1];
-#pragma unroll
-    for (int i = 0; i <= RPT; ++i) acc[i] = 0.f;
-    const float* pr = tile + tx * ks;
-    for (int d = 0; d < dk; d += 4) {
-      const float4 pv = *reinterpret_cast<const float4*>(pr + d);
-#pragma unroll
-      for (int i = 0; i <= RPT; ++i) {
-        const float4 q = *reinterpret_cast<const float4*>(qv + (ty * RPT + i) * dk + d);
-        acc[i] += (q.x * pv.x + q.y * pv.y) + (q.z * pv.z + q.w * pv.w);
-      }
-    }
-    const int n = n0 + tx;
-    if (n < T) {
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int r = ty * RPT + i;
-        const int a = a0 + r;
-        if (a < T) {
-          const int b1 = n - (T - 1 - a);
-          if (b1 >= 0 && b1 <= a) S[r * t_pad + b1] += acc[i];
-          const int b2 = n + a + 2;
-          if (b2 < T) S[r * t_pad + b2] += acc[i + 1];
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- phase C: softmax over keys (scores / sqrt(dk))
-  {
-    const float scale = rsqrtf(static_cast<float>(dk));
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < R; r += ATT_THREADS / 32) {
-      if (a0 + r >= T) continue;
-      float* row = S + r * t_pad;
-      float m = -INFINITY;
-      for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
-      m = warp_max(m) * scale;
-      float sum = 0.f;
-      for (int j = lane; j < T; j += 32) {
-        const float e = expf(row[j] * scale - m);
-        row[j] = e;
-        sum += e;
-      }
-      const float inv = 1.0f / warp_sum(sum);
-      for (int j = lane; j < T; j += 32) row[j] *= inv;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase D: ctx = P . V
-  float ctx[RPT][4];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
-  for (int k0 = 0; k0 < T; k0 += ATT_TK) {
-    for (int i = tid; i < ATT_TK * dk4; i += ATT_THREADS) {
-      const int kk = i / dk4, d4 = i - kk * dk4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + kk < T) v = *reinterpret_cast<const float4*>(qkv + (base + k0 + kk) * ld3 + 2 * d_model + h * dk + d4 * 4);
-      *reinterpret_cast<float4*>(tile + kk * ks + d4 * 4) = v;
-    }
-    __syncthreads();
-    const int kn = min(ATT_TK, T - k0);
-    for (int kk = 0; kk < kn; ++kk) {
-      float p[RPT];
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) p[i] = S[(ty * RPT + i) * t_pad + k0 + kk];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int d = tx + 64 * j;
-        if (d < dk) {
-          const float v = tile[kk * ks + d];
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) ctx[i][j] += p[i] * v;
-        }
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    const int a = a0 + ty * RPT + i;
-    if (a >= T) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int d = tx + 64 * j;
-      if (d < dk) {
-        bf16 hh, ll;
-        split_op16(ctx[i][j], hh, ll);
-        out_hi[(base + a) * out_ld + h * dk + d] = hh;
-        if (out_lo) out_lo[(base + a) * out_ld + h * dk + d] = ll;
-      }
-    }
-  }
-}
-
-template <int R>
-static int launch_attention(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
-                            int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld,
-                            cudaStream_t s) {
-  const int dk = d_model / n_head;
-  const int t_pad = round_up(max_len, 4) + 4;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(R) * dk + (R + 1) * dk + static_cast<size_t>(R) * t_pad +
-                                       ATT_TK * (dk + 4));
-  JB_REQUIRE(smem <= 227 * 1024, -2, "attention: utterance too long for shared memory");
-  auto kern = relpos_attention_kernel<R>;
-  JB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid(ceil_div(max_len, R), L.nseg, n_head);
-  kern<<<grid, ATT_THREADS, smem, s>>>(qkv, pos, bias_u, bias_v, d_model, dk, L, t_pad, out_hi, out_lo, out_ld);
-  JB_KERNEL_OK();
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Register-tiled variant for utterances up to ~440 positions (every shipped workload): one CTA =
-// 64 query rows x (utterance, head), 256 threads, 4 rows x 4 keys per thread in the two score passes
-// (8 FMA per shared-memory load instead of 3.2), float4-along-keys in the P.V pass.  The bias terms are
-// split off the dot products: (q+u).k = q.k + u.k and (q+v).p = q.p + v.p, so one copy of the 65 query
-// rows serves both passes; u.k / v.p are one extra 192-long dot per key / position of each tile.
-// ------------------------------------------------------------------------------------------------
-static constexpr int ATT64_R = 64;
-
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-relpos_attention64_kernel(const float* __restrict__ qkv, const float* __restrict__ pos,
-                          const float* __restrict__ bias_u, const float* __restrict__ bias_v, int d_model, int dk,
-                          RowLayout L, int t_pad, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int out_ld) {
-  constexpr int R = ATT64_R;
-  const int b = blockIdx.y, h = blockIdx.z;
-  const int T = L.seg_len[b];
-  const int a0 = blockIdx.x * R;
-  if (a0 >= T) return;
-  const long long base = L.seg_start[b];
-  const int ks = dk + 4;
-  extern __shared__ float sm[];
-  float* q = sm;                         // [R+1][ks]   raw queries (row R = first row of the next tile)
-  float* S = q + (R + 1) * ks;           // [R][t_pad]
-  float* tile = S + R * t_pad;           // [ATT_TK][ks]
-  float* cvec = tile + ATT_TK * ks;      // [ATT_TK]    u.k (pass A) / v.p (pass B) of the tile
-  float* ub = cvec + ATT_TK;             // [dk] bias_u of this head, then [dk] bias_v
-  const int tid = threadIdx.x;
-  const int ld3 = 3 * d_model;
-  const int dk4 = dk >> 2;
-  const int tx = tid & 15, ty = tid >> 4;   // 16 key lanes (4 keys each: tx, tx+16, tx+32, tx+48), 16 row groups of 4
-
-  for (int i = tid; i < (R + 1) * dk4; i += ATT_THREADS) {
-    const int r = i / dk4, d4 = i - r * dk4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a0 + r < T) v = *reinterpret_cast<const float4*>(qkv + (base + a0 + r) * ld3 + h * dk + d4 * 4);
-    *reinterpret_cast<float4*>(q + r * ks + d4 * 4) = v;
-  }
-  for (int i = tid; i < 2 * dk; i += ATT_THREADS) ub[i] = i < dk ? bias_u[h * dk + i] : bias_v[h * dk + i - dk];
-  __syncthreads();
-
-  // load one 64-row tile of k / p / v (zero rows past T) and, for the score passes, bias . row
-  auto load_tile = [&](const float* src, long long row_stride, int r0, const float* bias_vec) {
-    for (int i = tid; i < ATT_TK * dk4; i += ATT_THREADS) {
-      const int kk = i / dk4, d4 = i - kk * dk4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + kk < T) v = *reinterpret_cast<const float4*>(src + static_cast<long long>(r0 + kk) * row_stride + d4 * 4);
-      *reinterpret_cast<float4*>(tile + kk * ks + d4 * 4) = v;
-    }
-    __syncthreads();
-    if (bias_vec) {
-      const int kk = tid >> 2, part = tid & 3;   // 4 threads per row, dk/4 elements each
-      float acc = 0.f;
-      const int per = dk >> 2;
-      for (int d = part * per; d < (part + 1) * per; ++d) acc += tile[kk * ks + d] * bias_vec[d];
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (part == 0) cvec[kk] = acc;
-      __syncthreads();
-    }
-  };
-
-  // ---- pass A: S[r][key] = q_a . k_key + u . k_key
-  for (int k0 = 0; k0 < T; k0 += ATT_TK) {
-    load_tile(qkv + base * ld3 + d_model + h * dk, ld3, k0, ub);
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int d = 0; d < dk; d += 4) {
-      float4 qv[4], kv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(q + (ty * 4 + i) * ks + d);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4*>(tile + (tx + 16 * j) * ks + d);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          acc[i][j] += (qv[i].x * kv[j].x + qv[i].y * kv[j].y) + (qv[i].z * kv[j].z + qv[i].w * kv[j].w);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int key = k0 + tx + 16 * j;
-      if (key < T) {
-        const float cu = cvec[tx + 16 * j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) S[(ty * 4 + i) * t_pad + key] = acc[i][j] + cu;
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- pass B: BD[a][n] = q_a . p_n + v . p_n, scattered through the closed-form legacy rel-shift
-  for (int n0 = 0; n0 < T; n0 += ATT_TK) {
-    load_tile(pos + h * dk, d_model, n0, ub + dk);
-    float acc[5][4];   // rows ty*4 .. ty*4+4 (the extra row feeds the "a+1" branch of the shift)
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int d = 0; d < dk; d += 4) {
-      float4 qv[5], pv[4];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) qv[i] = *reinterpret_cast<const float4*>(q + (ty * 4 + i) * ks + d);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) pv[j] = *reinterpret_cast<const float4*>(tile + (tx + 16 * j) * ks + d);
-#pragma unroll
-      for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          acc[i][j] += (qv[i].x * pv[j].x + qv[i].y * pv[j].y) + (qv[i].z * pv[j].z + qv[i].w * pv[j].w);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx + 16 * j;
-      if (n < T) {
-        const float cv = cvec[tx + 16 * j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = ty * 4 + i;
-          const int a = a0 + r;
-          if (a < T) {
-            const int b1 = n - (T - 1 - a);
-            if (b1 >= 0 && b1 <= a) S[r * t_pad + b1] += acc[i][j] + cv;
-            const int b2 = n + a + 2;
-            if (b2 < T) S[r * t_pad + b2] += acc[i + 1][j] + cv;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- softmax over keys (scores / sqrt(dk))
-  {
-    const float scale = rsqrtf(static_cast<float>(dk));
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < R; r += ATT_THREADS / 32) {
-      if (a0 + r >= T) continue;
-      float* row = S + r * t_pad;
-      float m = -INFINITY;
-      for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
-      m = warp_max(m) * scale;
-      float sum = 0.f;
-      for (int j = lane; j < T; j += 32) {
-        const float e = expf(row[j] * scale - m);
-        row[j] = e;
-        sum += e;
-      }
-      const float inv = 1.0f / warp_sum(sum);
-      for (int j = lane; j < T; j += 32) row[j] *= inv;
-      for (int j = T + lane; j < t_pad; j += 32) row[j] = 0.f;   // the P.V pass reads keys in groups of 4
-    }
-  }
-  __syncthreads();
-
-  // ---- ctx = P . V : thread = (16-row group, dim lane), 3 dims (d, d+64, d+128), keys 4 at a time
-  const int dx = tid & 63, rg = tid >> 6;
-  float ctx[16][4];
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
-  for (int k0 = 0; k0 < T; k0 += ATT_TK) {
-    load_tile(qkv + base * ld3 + 2 * d_model + h * dk, ld3, k0, nullptr);
-    const int kn = min(ATT_TK, T - k0);
-    for (int kk = 0; kk < kn; kk += 4) {
-      float vv[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int d = dx + 64 * j;
-          vv[u][j] = d < dk ? tile[(kk + u) * ks + d] : 0.f;   // rows past T are zero-filled
-        }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 p = *reinterpret_cast<const float4*>(S + (rg * 16 + i) * t_pad + k0 + kk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          ctx[i][j] += (p.x * vv[0][j] + p.y * vv[1][j]) + (p.z * vv[2][j] + p.w * vv[3][j]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int a = a0 + rg * 16 + i;
-    if (a >= T) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int d = dx + 64 * j;
-      if (d < dk) {
-        bf16 hh, ll;
-        split_op16(ctx[i][j], hh, ll);
-        out_hi[(base + a) * out_ld + h * dk + d] = hh;
-        if (out_lo) out_lo[(base + a) * out_ld + h * dk + d] = ll;
-      }
-    }
-  }
-}
-
-static int launch_attention64(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
-                              int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld,
-                              cudaStream_t s, bool* launched) {
-  const int dk = d_model / n_head;
-  const int t_pad = round_up(max_len, 4) + 4;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(ATT64_R + 1) * (dk + 4) + static_cast<size_t>(ATT64_R) * t_pad +
-                                       ATT_TK * (dk + 4) + ATT_TK + 2 * dk);
-  *launched = false;
-  if (smem > 227 * 1024 || (dk & 15) != 0) return 0;   // too long for this variant: caller falls back
-  static size_t attr = 0;
-  if (smem > attr) {
-    JB_CUDA_OK(cudaFuncSetAttribute(relpos_attention64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
-  dim3 grid(ceil_div(max_len, ATT64_R), L.nseg, n_head);
-  relpos_attention64_kernel<<<grid, ATT_THREADS, smem, s>>>(qkv, pos, bias_u, bias_v, d_model, dk, L, t_pad, out_hi, out_lo, out_ld);
-  JB_KERNEL_OK();
-  *launched = true;
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Tensor-core variant (legacy warp-level MMA, m16n8k8 TF32) with the 3xTF32 split: x = hi + lo with
-// hi = x truncated to TF32 (exact remainder lo = x - hi, rounded to TF32); a.b ~= hi.hi + hi.lo + lo.hi
-// accumulated in fp32, which keeps scores and context FP32-faithful (the dropped lo.lo term is ~2^-21
-// relative).  tcgen05 is not used here: the operands are per-(utterance, head) 64 x d_k tiles that need a
-// register-level split and a scatter epilogue (the rel-shift), which the warp-level fragment layout gives
-// directly.
-//
-// One CTA = 64 query rows a0..a0+63 of one (utterance, head), of which it OWNS the first 63: the legacy
-// rel-shift sends BD[a'][n] = (q_a' + v) . p_n to row a' (keys <= a') and to row a'-1 (keys >= a'+1), so
-// row r is complete once BD rows r and r+1 are known; tiles advance by 63 rows and the 64th row only
-// contributes its BD.  8 warps = 4 row blocks of 16 x 2 halves of the 64-key tile (score passes) or of the
-// head dimension (P.V pass).  The biases are added while the A fragments are built ((q+u).k, (q+v).p as
-// the reference computes them).  The next k / p / v tile is prefetched into registers while the current
-// one is in the MMAs.  Shared-memory strides: d_k+4 (== 4 mod 32) for operands read as [g][t], d_k+8
-// (== 8 mod 32) for the V tile read as [t][g], t_pad with t_pad/4 odd: fragment loads are conflict-free.
-// ------------------------------------------------------------------------------------------------
-static constexpr int ATT_MMA_OWN = 63;
-
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;   // the MMA ignores the low 13 bits: +half ulp = round
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], float b0,
-                                           float b1) {
-  uint32_t b0h, b0l, b1h, b1l;
-  split_tf32(b0, b0h, b0l);
-  split_tf32(b1, b1h, b1l);
-  mma_tf32(c, alo, b0h, b1h);
-  mma_tf32(c, ahi, b0l, b1l);
-  mma_tf32(c, ahi, b0h, b1h);
-}
-
-template <int DK>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-relpos_attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ pos,
-                            const float* __restrict__ bias_u, const float* __restrict__ bias_v, int d_model,
-                            RowLayout L, int t_pad, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int out_ld) {
-  constexpr int R = 64;
-  constexpr int KS = DK + 4;    // q / k / p row stride (words)
-  constexpr int KV = DK + 8;    // v row stride
-  constexpr int DK4 = DK / 4;
-  constexpr int NT_C = DK / 16; // 8-wide n-tiles per warp in the P.V pass
-  constexpr int NPRE = ATT_TK * DK4 / ATT_THREADS;   // float4 per thread per tile
-  static_assert(ATT_TK * DK4 % ATT_THREADS == 0, "tile must divide evenly over the CTA");
-  const int b = blockIdx.y, h = blockIdx.z;
-  const int T = L.seg_len[b];
-  const int a0 = blockIdx.x * ATT_MMA_OWN;
-  if (a0 >= T) return;
-  const long long base = L.seg_start[b];
-  extern __shared__ float sm[];
-  float* q = sm;                         // [R][KS]
-  float* S = q + R * KS;                 // [R][t_pad]
-  float* tile = S + R * t_pad;           // [ATT_TK][KV]
-  float* ub = tile + ATT_TK * KV;        // [2*DK] bias_u, bias_v of this head
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int rb = warp & 3, half = warp >> 2;
-  const int ld3 = 3 * d_model;
-  const int n_tiles = (T + ATT_TK - 1) / ATT_TK;
-
-  // tile jobs: n_tiles of k, n_tiles of p, n_tiles of v; job j+1 is fetched while job j is computed
-  float4 pre[NPRE];
-  auto fetch = [&](int job) {
-    const int pass = job / n_tiles, r0 = (job - pass * n_tiles) * ATT_TK;
-    const float* src = pass == 1 ? pos + h * DK : qkv + base * ld3 + (pass == 0 ? d_model : 2 * d_model) + h * DK;
-    const long long row_stride = pass == 1 ? d_model : ld3;
-#pragma unroll
-    for (int i = 0; i < NPRE; ++i) {
-      const int idx = tid + i * ATT_THREADS;
-      const int kk = idx / DK4, d4 = idx - kk * DK4;
-      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + kk < T) pre[i] = *reinterpret_cast<const float4*>(src + static_cast<long long>(r0 + kk) * row_stride + d4 * 4);
-    }
-  };
-  auto commit = [&](int stride) {
-#pragma unroll
-    for (int i = 0; i < NPRE; ++i) {
-      const int idx = tid + i * ATT_THREADS;
-      const int kk = idx / DK4, d4 = idx - kk * DK4;
-      *reinterpret_cast<float4*>(tile + kk * stride + d4 * 4) = pre[i];
-    }
-  };
-
-  fetch(0);
-  for (int i = tid; i < R * DK4; i += ATT_THREADS) {
-    const int r = i / DK4, d4 = i - r * DK4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a0 + r < T) v = *reinterpret_cast<const float4*>(qkv + (base + a0 + r) * ld3 + h * DK + d4 * 4);
-    *reinterpret_cast<float4*>(q + r * KS + d4 * 4) = v;
-  }
-  for (int i = tid; i < 2 * DK; i += ATT_THREADS) ub[i] = i < DK ? bias_u[h * DK + i] : bias_v[h * DK + i - DK];
-
-  // 16 rows (rb) x 32 tile rows (half) x DK:  acc[nt] = (q + bias) . tile^T
-  auto score_tile = [&](float (&acc)[4][4], const float* bias) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const float* qa = q + (rb * 16 + g) * KS + t;
-    const float* kb = tile + (half * 32 + g) * KS + t;
-    const float* bv = bias + t;
-#pragma unroll 4
-    for (int k = 0; k < DK; k += 8) {
-      uint32_t ahi[4], alo[4];
-      const float u0 = bv[k], u1 = bv[k + 4];
-      split_tf32(qa[k] + u0, ahi[0], alo[0]);
-      split_tf32(qa[8 * KS + k] + u0, ahi[1], alo[1]);
-      split_tf32(qa[k + 4] + u1, ahi[2], alo[2]);
-      split_tf32(qa[8 * KS + k + 4] + u1, ahi[3], alo[3]);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mma_3xtf32(acc[nt], ahi, alo, kb[nt * 8 * KS + k], kb[nt * 8 * KS + k + 4]);
-    }
-  };
-
-  int job = 0;
-  // ---- pass A: S[r][key] = (q_a + u) . k_key
-  for (int k0 = 0; k0 < T; k0 += ATT_TK, ++job) {
-    commit(KS);
-    __syncthreads();
-    fetch(job + 1);
-    float acc[4][4];
-    score_tile(acc, ub);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = rb * 16 + g + (e >> 1) * 8;
-        const int key = k0 + half * 32 + nt * 8 + 2 * t + (e & 1);
-        if (key < T) S[r * t_pad + key] = acc[nt][e];
-      }
-    __syncthreads();
-  }
-
-  // ---- pass B: BD[a'][n] = (q_a' + v) . p_n lands in row a' (keys <= a') and row a'-1 (keys >= a'+1)
-  for (int n0 = 0; n0 < T; n0 += ATT_TK, ++job) {
-    commit(KS);
-    __syncthreads();
-    fetch(job + 1);
-    float acc[4][4];
-    score_tile(acc, ub + DK);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = rb * 16 + g + (e >> 1) * 8;
-        const int n = n0 + half * 32 + nt * 8 + 2 * t + (e & 1);
-        const int a = a0 + r;
-        if (n < T && a < T) {
-          const int b1 = n - (T - 1 - a);
-          if (b1 >= 0 && b1 <= a) S[r * t_pad + b1] += acc[nt][e];
-          const int b2 = n + a + 1;
-          if (r > 0 && b2 < T) S[(r - 1) * t_pad + b2] += acc[nt][e];
-        }
-      }
-    __syncthreads();
-  }
-
-  // ---- softmax over keys (scores / sqrt(dk)); the first v tile is already in flight
-  {
-    const float scale = rsqrtf(static_cast<float>(DK));
-    for (int r = warp; r < R; r += ATT_THREADS / 32) {
-      float* row = S + r * t_pad;
-      if (r >= ATT_MMA_OWN || a0 + r >= T) {   // rows that are not stored still enter the MMA: keep them finite
-        for (int j = lane; j < t_pad; j += 32) row[j] = 0.f;
-        continue;
-      }
-      float m = -INFINITY;
-      for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
-      m = warp_max(m) * scale;
-      float sum = 0.f;
-      for (int j = lane; j < T; j += 32) {
-        const float e = expf(row[j] * scale - m);
-        row[j] = e;
-        sum += e;
-      }
-      const float inv = 1.0f / warp_sum(sum);
-      for (int j = lane; j < T; j += 32) row[j] *= inv;
-      for (int j = T + lane; j < t_pad; j += 32) row[j] = 0.f;
-    }
-  }
-
-  // ---- ctx = P . V : warp = 16 rows x DK/2 dims
-  float ctx[NT_C][4];
-#pragma unroll
-  for (int i = 0; i < NT_C; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
-  for (int k0 = 0; k0 < T; k0 += ATT_TK, ++job) {
-    commit(KV);
-    __syncthreads();
-    if (job + 1 < 3 * n_tiles) fetch(job + 1);
-    const int kn = min(ATT_TK, T - k0);
-    const float* pa = S + (rb * 16 + g) * t_pad + k0 + t;
-    const float* vb = tile + t * KV + half * (DK / 2) + g;
-    for (int kk = 0; kk < kn; kk += 8) {
-      uint32_t ahi[4], alo[4];
-      split_tf32(pa[kk], ahi[0], alo[0]);
-      split_tf32(pa[8 * t_pad + kk], ahi[1], alo[1]);
-      split_tf32(pa[kk + 4], ahi[2], alo[2]);
-      split_tf32(pa[8 * t_pad + kk + 4], ahi[3], alo[3]);
-#pragma unroll
-      for (int nt = 0; nt < NT_C; ++nt) mma_3xtf32(ctx[nt], ahi, alo, vb[kk * KV + nt * 8], vb[(kk + 4) * KV + nt * 8]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int nt = 0; nt < NT_C; ++nt)
-#pragma unroll
-    for (int hr = 0; hr < 2; ++hr) {
-      const int r = rb * 16 + g + hr * 8;
-      const int a = a0 + r;
-      if (r >= ATT_MMA_OWN || a >= T) continue;
-      const int d = half * (DK / 2) + nt * 8 + 2 * t;
-      bf16 h0, l0, h1, l1;
-      split_op16(ctx[nt][hr * 2], h0, l0);
-      split_op16(ctx[nt][hr * 2 + 1], h1, l1);
-      const long long o = (base + a) * out_ld + h * DK + d;
-      *reinterpret_cast<uint32_t*>(out_hi + o) =
-          static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-      if (out_lo)
-        *reinterpret_cast<uint32_t*>(out_lo + o) =
-            static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-    }
-}
-
-template <int DK>
-static int launch_attention_mma(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
-                                int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld,
-                                cudaStream_t s, bool* launched) {
-  const int t_pad = round_up(max_len, 8) + 4;   // t_pad / 4 odd
-  const size_t smem = sizeof(float) * (static_cast<size_t>(64) * (DK + 4) + static_cast<size_t>(64) * t_pad +
-                                       ATT_TK * (DK + 8) + 2 * DK);
-  *launched = false;
-  if (smem > 227 * 1024 || (out_ld & 1)) return 0;
-  static size_t attr = 0;
-  if (smem > attr) {
-    JB_CUDA_OK(cudaFuncSetAttribute(relpos_attention_mma_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
-  dim3 grid(ceil_div(max_len, ATT_MMA_OWN), L.nseg, n_head);
-  relpos_attention_mma_kernel<DK><<<grid, ATT_THREADS, smem, s>>>(qkv, pos, bias_u, bias_v, d_model, L, t_pad, out_hi, out_lo, out_ld);
-  JB_KERNEL_OK();
-  *launched = true;
-  return 0;
-}
-
-int relpos_attention(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
-                     int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s) {
-  const int dk = d_model / n_head;
-  JB_REQUIRE(dk * n_head == d_model && dk % 4 == 0 && dk <= 256, -2, "attention: d_k must be a multiple of 4, <= 256");
-  if (L.nseg == 0 || max_len == 0) return 0;
-  if (!getenv("JATTS_B200_NO_ATT_MMA")) {
-    bool launched = false;
-    switch (dk) {
-      case 32: JB_PROPAGATE(launch_attention_mma<32>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched)); break;
-      case 64: JB_PROPAGATE(launch_attention_mma<64>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched)); break;
-      case 128: JB_PROPAGATE(launch_attention_mma<128>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched)); break;
-      case 192: JB_PROPAGATE(launch_attention_mma<192>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched)); break;
-      default: break;
-    }
-    if (launched) return 0;
-  }
-  {
-    bool launched = false;
-    JB_PROPAGATE(launch_attention64(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s, &launched));
-    if (launched) return 0;
-  }
-  if (max_len <= 1800) return launch_attention<16>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
-  if (max_len <= 4000) return launch_attention<8>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
-  return launch_attention<4>(qkv, pos, bias_u, bias_v, n_head, d_model, L, max_len, out_hi, out_lo, out_ld, s);
-}
-
-// ------------------------------------------------------------------------------------------------
 // depthwise conv + folded BatchNorm + Swish
 // ------------------------------------------------------------------------------------------------
 __global__ void dwconv_swish_kernel(const float* __restrict__ g, int c, const float* __restrict__ wT,

@@ -26,10 +26,15 @@ int split_rows(const float* x, int c, RowLayout L, bf16* hi, bf16* lo, int bf_ld
 int ln_dot_rows(const float* x, int c, const float* gamma, const float* beta, float eps, const float* w, float b,
                 RowLayout L, float* out, cudaStream_t s);
 
-// legacy relative-position self attention core (attention.py:164-206) for every utterance/head.
-// qkv: [rows, 3*D] fp32 (q | k | v), pos: [>= max_len, D] fp32 = linear_pos(pe)[n], out: hi/lo bf16 [rows, ld]
-int relpos_attention(const float* qkv, const float* pos, const float* bias_u, const float* bias_v, int n_head,
-                     int d_model, RowLayout L, int max_len, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s);
+// legacy relative-position self attention core (attention.py:164-206) for every utterance / head, on tcgen05 tensor
+// cores (attention_tc.cu).  x: [x_rows, 4*D] fp16 (hi, lo*2^11) pairs per row = [q + bias_u | q + bias_v | k | v] as
+// the fused projection GEMM writes them; pos: [pos_rows, D] pair = linear_pos(pe); out: (hi, lo) pair [rows, out_ld].
+// scratch: relpos_attention_scratch_bytes(max_len, nseg, n_head) bytes of device memory (per-CTA score rows).
+bool relpos_attention_supported(int n_head, int d_model);
+size_t relpos_attention_scratch_bytes(int max_len, int nseg, int n_head);
+int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const bf16* pos_hi, const bf16* pos_lo,
+                     int pos_rows, int n_head, int d_model, RowLayout L, int max_len, float* scratch,
+                     size_t scratch_bytes, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s);
 
 // depthwise Conv1d (BatchNorm folded into wT/bias on the host) -> Swish (convolution.py:74-75)
 // g: [rows, C] fp32 (GLU output), wT: [k][C], out: hi/lo bf16

@@ -45,7 +45,7 @@ JVS_FS2 = dict(JSUT_FS2, spk_embed_dim=192, spk_embed_integration_type="add")
 
 # a shrunken config with the same structure, for CPU-speed tests of host logic
 TINY_FS2 = dict(
-    JSUT_FS2, idim=20, adim=64, eunits=128, dunits=128, elayers=1, dlayers=1,
+    JSUT_FS2, idim=20, adim=64, aheads=1, eunits=128, dunits=128, elayers=1, dlayers=1,
     duration_predictor_chans=64, pitch_predictor_chans=64, pitch_predictor_layers=2,
     energy_predictor_chans=64, postnet_chans=64, postnet_layers=3,
 )

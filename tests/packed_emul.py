@@ -39,17 +39,18 @@ def ln(p, name, x):
     return F.layer_norm(x, (x.shape[-1],), p[name + ".g"], p[name + ".b"], 1e-12)
 
 
-def rel_attention(p, pre, qkv, n_head):
-    t, d3 = qkv.shape
-    d = d3 // 3
+def rel_attention(p, pre, x4, n_head):
+    """x4 = projection output [q + bias_u | q + bias_v | k | v]; pos table as an fp16 (hi, lo * 2^11) pair"""
+    t, d4 = x4.shape
+    d = d4 // 4
     dk = d // n_head
-    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
-    pos = p[pre + "pos"][:t]
+    q_u, q_v, k, v = x4[:, :d], x4[:, d:2 * d], x4[:, 2 * d:3 * d], x4[:, 3 * d:]
+    pos = (p[pre + "pos.hi"].float() + p[pre + "pos.lo"].float() / 2048.0)[:t]
     out = torch.zeros(t, d)
     for h in range(n_head):
         sl = slice(h * dk, (h + 1) * dk)
-        qu = q[:, sl] + p[pre + "bias_u"][sl]
-        qv = q[:, sl] + p[pre + "bias_v"][sl]
+        qu = q_u[:, sl]
+        qv = q_v[:, sl]
         ac = qu @ k[:, sl].t()
         bd = qv @ pos[:, sl].t()
         sh = torch.zeros(t, t)
@@ -71,7 +72,7 @@ def conformer(p, pre, x, n_layers, n_head, units):
         h = ln(p, q + "ln_ffm", x)
         x = x + 0.5 * conv(p, q + "ffm_w2", torch.relu(conv(p, q + "ffm_w1", h, units)), d)
         h = ln(p, q + "ln_mha", x)
-        x = x + conv(p, q + "out", rel_attention(p, q, conv(p, q + "qkv", h, 3 * d), n_head), d)
+        x = x + conv(p, q + "out", rel_attention(p, q, conv(p, q + "qkv", h, 4 * d), n_head), d)
         h = ln(p, q + "ln_conv", x)
         g2 = conv(p, q + "pw1", h, 2 * d)  # interleaved [64 a | 64 gate] per 128 tile
         g2 = g2.view(-1, d // 64, 2, 64)
