@@ -29,6 +29,7 @@
 #include "tc_common.cuh"
 
 namespace jb {
+extern long long* g_trace_ptr;   // conv_gemm_tc2.cu
 namespace {
 
 constexpr int kAttThreads = 320;
@@ -41,7 +42,9 @@ constexpr int kRegionX = kMaxNC * kStageB;    // Q (one stage per 64-wide d_k ch
 constexpr int kRegionY = kRingB * kStageB;    // K / position ring; later the two V stages
 constexpr int kVBlock = 64 * 128;             // [64 keys x 64 dims] 8 KB
 constexpr int kVStage = 2 * kMaxNC * kVBlock; // hi blocks then lo blocks: 48 KB
-constexpr int kSmemBytes = kRegionX + kRegionY + 1024 /*barriers*/ + 1024 /*alignment*/;
+constexpr int kStgPitch = 20;                // staging row pitch in words: 16 data + 4 pad (conflict-free 128-bit rows)
+constexpr int kStgBytes = 32 * kStgPitch * 4;   // one worker warp's [32 rows x 16 words] transpose buffer
+constexpr int kSmemBytes = kRegionX + kRegionY + 1024 /*barriers*/ + 8 * kStgBytes + 1024 /*alignment*/;
 static_assert(2 * kVStage <= kRegionY && 2 * kStageB <= kRegionX, "phase-3 buffers alias the phase-1/2 regions");
 
 struct AttParams {
@@ -55,7 +58,13 @@ struct AttParams {
   bf16* out_lo;
   int out_ld;
   float scale;       // 1 / sqrt(d_k)
+  long long* trace;  // debug: clock64 stamps of CTA 0 (jatts_debug_set_trace), else null
 };
+
+#define ATR(slot, idx)                                                                                       \
+  do {                                                                                                       \
+    if (P.trace && blockIdx.x == 0 && (idx) < 8) P.trace[(slot) * 8 + (idx)] = clock64();                    \
+  } while (0)
 
 struct TileInfo {
   int h, a0, T, seg0;
@@ -82,8 +91,19 @@ __host__ __device__ constexpr uint32_t att_idesc(int n, bool b_mn_major) {
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_f16_bits(bf16 a, bf16 b) {   // two 16-bit patterns -> one word
-  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, 2 ulp; 2^-inf = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two values -> packed fp16 (hi, hi) and (lo', lo') words of the split operand pair (common.cuh::split_op16 without
+// the saturation: probabilities and convex combinations of fp16-representable values cannot overflow)
+__device__ __forceinline__ void split_pair16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * kSplitScale, (b - hf.y) * kSplitScale);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __global__ void __launch_bounds__(kAttThreads, 1)
@@ -110,6 +130,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
   uint64_t* v_full = bars + 19;    // [2]
   uint64_t* v_empty = bars + 21;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  uint8_t* stg_base = Y + kRegionY + 1024;   // [8 worker warps][kStgBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,10 +140,10 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
     tma_prefetch_desc(&tm_v_hi); tma_prefetch_desc(&tm_v_lo);
     tma_prefetch_desc(&tm_p_hi); tma_prefetch_desc(&tm_p_lo);
     mbar_init(q_full, 1); mbar_init(q_free, 1); mbar_init(s2_done, 1); mbar_init(ctx_full, 1);
-    mbar_init(tile_free, 4);
+    mbar_init(tile_free, 8);
     for (int i = 0; i < kRingB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
       mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
@@ -150,6 +171,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
         const int nkt = (ti.T + 127) >> 7, nkc = (ti.T + 63) >> 6;
         const int hcol = ti.h * P.dk;
         if (it > 0) mbar_wait(ctx_full, (it - 1) & 1);   // every MMA of the previous tile has read its operands
+        ATR(0, it);
         auto load_q = [&](int which) {
           mbar_expect_tx(q_full, static_cast<uint32_t>(P.nc) * kStageB);
           for (int c = 0; c < P.nc; ++c) {
@@ -169,10 +191,13 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
         };
         load_q(0);                                                                         // q + bias_u
         for (int j = 0; j < nkt; ++j) load_b(&tm_x_hi, &tm_x_lo, 2 * D + hcol, ti.seg0 + j * 128);   // keys
+        ATR(1, it);
         mbar_wait(q_free, it & 1);                                                         // phase-1 MMAs done with Q
+        ATR(2, it);
         load_q(1);                                                                         // q + bias_v
         for (int j = 0; j < nkt; ++j) load_b(&tm_p_hi, &tm_p_lo, hcol, j * 128);           // positions 0 .. T-1
         mbar_wait(s2_done, it & 1);                                                        // ring and Q regions are free
+        ATR(3, it);
         for (int kc = 0; kc < nkc; ++kc) {
           const uint32_t st = nv & 1;
           mbar_wait(&v_empty[st], ((nv >> 1) & 1) ^ 1);
@@ -183,13 +208,13 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
           }
           ++nv;
         }
+        ATR(4, it);
         ++it;
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     if (elect_one()) {
-      constexpr uint32_t idesc_s = att_idesc(128, false);
       const uint32_t idesc_c = att_idesc(P.dk, true);
       constexpr uint32_t desc_hi = static_cast<uint32_t>(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, v1, SWIZZLE_128B
       constexpr uint32_t k_lo0 = 1u << 16;                                      // K-major: LBO unused
@@ -202,15 +227,19 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
         const int nkt = (ti.T + 127) >> 7, nkc = (ti.T + 63) >> 6;
         if (it > 0) mbar_wait(tile_free, (it - 1) & 1);   // the context accumulators of the previous tile were read
         tc_fence_after();
+        ATR(8, it);
         for (int ph = 0; ph < 2; ++ph) {
           mbar_wait(q_full, qf & 1);
           ++qf;
           tc_fence_after();
+          ATR(9 + 2 * ph, it);
           for (int j = 0; j < nkt; ++j) {
             const uint32_t buf = sb & 1;
             mbar_wait(&s_empty[buf], ((sb >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_main = tmem_base + buf * 256u, d_corr = d_main + 128u;
+            // the last key / position tile only computes the 16-column groups that hold real keys
+            const uint32_t idesc_j = att_idesc(min(128, round_up(ti.T - j * 128, 16)), false);
             for (int c = 0; c < P.nc; ++c) {
               const uint32_t st = nb % kRingB;
               mbar_wait(&b_full[st], (nb / kRingB) & 1);
@@ -221,9 +250,9 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
                 const uint32_t ah = k_lo0 + ((a0 + k * 32) >> 4), al = k_lo0 + ((a0 + kTile16 + k * 32) >> 4);
                 const uint32_t bh = k_lo0 + ((b0 + k * 32) >> 4), bl = k_lo0 + ((b0 + kTile16 + k * 32) >> 4);
                 const uint32_t acc = (c | k) != 0 ? 1u : 0u;
-                tc_mma_bf16_lohi(d_main, ah, desc_hi, bh, desc_hi, idesc_s, acc);
-                tc_mma_bf16_lohi(d_corr, ah, desc_hi, bl, desc_hi, idesc_s, acc);
-                tc_mma_bf16_lohi(d_corr, al, desc_hi, bh, desc_hi, idesc_s, 1u);
+                tc_mma_bf16_lohi(d_main, ah, desc_hi, bh, desc_hi, idesc_j, acc);
+                tc_mma_bf16_lohi(d_corr, ah, desc_hi, bl, desc_hi, idesc_j, acc);
+                tc_mma_bf16_lohi(d_corr, al, desc_hi, bh, desc_hi, idesc_j, 1u);
               }
               tc_commit(&b_empty[st]);
               ++nb;
@@ -232,12 +261,14 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
             ++sb;
           }
           tc_commit(ph == 0 ? q_free : s2_done);
+          ATR(10 + 2 * ph, it);
         }
         for (int kc = 0; kc < nkc; ++kc) {
           const uint32_t pb = pc & 1, vs = nv & 1;
           mbar_wait(&p_full[pb], (pc >> 1) & 1);
           mbar_wait(&v_full[vs], (nv >> 1) & 1);
           tc_fence_after();
+          if (kc == 0) ATR(13, it);
           const uint32_t a0 = x_addr + pb * kStageB, b0 = y_addr + vs * kVStage;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 16 keys per MMA: 32 B along the A rows, two 8-key groups (2 KB) of V
@@ -254,14 +285,15 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
           ++nv;
         }
         tc_commit(ctx_full);
+        ATR(14, it);
         ++it;
       }
     }
   } else {
     // ============================ workers ============================
     const int w = warp - 2;            // 0..7: rows w*16 .. w*16+15 in the softmax / P phases
-    const int quad = warp & 3;         // TMEM lane quadrant this warp may read
-    const bool epi = w < 4;            // warps 2..5 cover quadrants 2, 3, 0, 1
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may read (warps 2..5 and 6..9 both cover 2,3,0,1)
+    const int hsel = w >> 2;           // which half of an accumulator's columns this warp moves in the epilogues
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int tp = P.tp;
     float* scr = P.scratch + static_cast<size_t>(blockIdx.x) * 2 * 128 * tp;
@@ -269,147 +301,235 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
     const float* BD = scr + static_cast<size_t>(128) * tp;
     const uint32_t x_addr = smem_u32(X);
     constexpr float kInvSplit = 1.0f / kSplitScale;
+    // staging tile of this warp: a thread owns one accumulator row (32 rows x 16 words + pad); the rows leave it
+    // 8 at a time, 4 lanes x 16 B per row, so that global stores are row-contiguous instead of 32 scattered pieces
+    const uint32_t stg = smem_u32(stg_base + w * kStgBytes);
+    const uint32_t stg_w = stg + static_cast<uint32_t>(lane * kStgPitch * 4);
+    const uint32_t stg_r = stg + static_cast<uint32_t>(((lane >> 2) * kStgPitch + (lane & 3) * 4) * 4);
+    const float sc2 = P.scale * 1.4426950408889634f;   // scores are kept in the log2 domain: p = 2^(s - max)
     uint32_t se = 0, pc = 0, it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileInfo ti = decode_tile(P, tile);
       if (!ti.valid) continue;
       const int T = ti.T, a0 = ti.a0;
       const int nkt = (T + 127) >> 7, nkc = (T + 63) >> 6;
-      // ---- score epilogue: TMEM (main + corr * 2^-11) -> scratch, thread = row
-      if (epi) {
-        const int r = quad * 32 + lane;
-        for (int ph = 0; ph < 2; ++ph) {
-          float* dst = scr + (static_cast<size_t>(ph) * 128 + r) * tp;
-          for (int j = 0; j < nkt; ++j) {
-            const uint32_t buf = se & 1;
-            mbar_wait(&s_full[buf], (se >> 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              uint32_t m[32], c[32];
-              tmem_ld32(lane_base + buf * 256u + static_cast<uint32_t>(ch * 32), m);
-              tmem_ld32(lane_base + buf * 256u + 128u + static_cast<uint32_t>(ch * 32), c);
-              tmem_ld_wait();
-              if (ch == 3) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[buf]);
-              }
-              float4* o = reinterpret_cast<float4*>(dst + j * 128 + ch * 32);
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                o[i] = make_float4(__uint_as_float(m[4 * i]) + __uint_as_float(c[4 * i]) * kInvSplit,
-                                   __uint_as_float(m[4 * i + 1]) + __uint_as_float(c[4 * i + 1]) * kInvSplit,
-                                   __uint_as_float(m[4 * i + 2]) + __uint_as_float(c[4 * i + 2]) * kInvSplit,
-                                   __uint_as_float(m[4 * i + 3]) + __uint_as_float(c[4 * i + 3]) * kInvSplit);
-            }
-            ++se;
+      const bool tr0 = warp == 2 && lane == 0, tr4 = warp == 6 && lane == 0;
+      if (tr0) ATR(16, it);
+      // ---- score epilogue: TMEM (main + corr * 2^-11) -> scratch; every warp moves 4 of the 8 16-column groups
+      for (int ph = 0; ph < 2; ++ph) {
+        float* dst = scr + (static_cast<size_t>(ph) * 128 + quad * 32 + (lane >> 2)) * tp + hsel * 64 + (lane & 3) * 4;
+        for (int j = 0; j < nkt; ++j) {
+          const uint32_t buf = se & 1;
+          mbar_wait(&s_full[buf], (se >> 1) & 1);
+          tc_fence_after();
+          if (tr0 && ph == 0 && j == 0) ATR(17, it);
+          const int ng = min(4, ((min(128, T - j * 128) + 15) >> 4) - hsel * 4);   // 16-column groups with real keys
+          if (ng <= 0) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[buf]);
           }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g >= ng) break;
+            uint32_t m[16], c[16];
+            tmem_ld16(lane_base + buf * 256u + static_cast<uint32_t>(hsel * 64 + g * 16), m);
+            tmem_ld16(lane_base + buf * 256u + 128u + static_cast<uint32_t>(hsel * 64 + g * 16), c);
+            tmem_ld_wait();
+            if (g == ng - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s_empty[buf]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 v;
+              v.x = __float_as_uint(__uint_as_float(m[4 * i]) + __uint_as_float(c[4 * i]) * kInvSplit);
+              v.y = __float_as_uint(__uint_as_float(m[4 * i + 1]) + __uint_as_float(c[4 * i + 1]) * kInvSplit);
+              v.z = __float_as_uint(__uint_as_float(m[4 * i + 2]) + __uint_as_float(c[4 * i + 2]) * kInvSplit);
+              v.w = __float_as_uint(__uint_as_float(m[4 * i + 3]) + __uint_as_float(c[4 * i + 3]) * kInvSplit);
+              sts128(stg_w + static_cast<uint32_t>(i * 16), v);
+            }
+            __syncwarp();
+            float* o = dst + j * 128 + g * 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // rows 8i .. 8i+7 of the warp's 32
+              const uint4 v = lds128(stg_r + static_cast<uint32_t>(i * 8 * kStgPitch * 4));
+              *reinterpret_cast<uint4*>(o + static_cast<size_t>(i * 8) * tp) = v;
+            }
+            __syncwarp();
+          }
+          ++se;
         }
       }
+      if (tr0) ATR(18, it);
+      if (tr4) ATR(24, it);
       __threadfence_block();
       named_bar_sync(1, 256);
-      // ---- softmax statistics, 16 rows per warp, lanes along the keys; the combined, scaled score replaces AC
+      if (tr0) ATR(19, it);
+      if (tr4) ATR(25, it);
+      // ---- softmax statistics: 16 rows per warp, two rows x 8 column blocks of loads in flight per lane; the
+      //      combined score (log2 domain) replaces AC in place; max / sum are online across 256-column chunks only
       float mrow[16], lrow[16];
 #pragma unroll
-      for (int rr = 0; rr < 16; ++rr) { mrow[rr] = -INFINITY; lrow[rr] = 0.f; }
-      for (int b0 = 0; b0 < T; b0 += 32) {
-        const int b = b0 + lane;
-        float sv[16];
+      for (int rp = 0; rp < 8; ++rp) {
+        float M[2], L[2];
+        float* pac[2];
+        const float* plo[2];
+        const float* phi[2];
+        int aa[2];
+        bool rok[2];
 #pragma unroll
-        for (int rr = 0; rr < 16; ++rr) {
-          const int r = w * 16 + rr, a = a0 + r;
-          float s = -INFINITY;
-          if (b < T && r < kOwnRows && a < T) {
-            float bd = 0.f;
-            if (b <= a) bd = BD[static_cast<size_t>(r) * tp + (T - 1 - a + b)];
-            else if (b >= a + 2) bd = BD[static_cast<size_t>(r + 1) * tp + (b - a - 2)];
-            s = (AC[static_cast<size_t>(r) * tp + b] + bd) * P.scale;
-            AC[static_cast<size_t>(r) * tp + b] = s;
-          }
-          sv[rr] = s;
-        }
-#pragma unroll
-        for (int rr = 0; rr < 16; ++rr) {
-          if (sv[rr] > -INFINITY) {
-            const float mn = fmaxf(mrow[rr], sv[rr]);
-            lrow[rr] = lrow[rr] * expf(mrow[rr] - mn) + expf(sv[rr] - mn);
-            mrow[rr] = mn;
+        for (int q = 0; q < 2; ++q) {
+          const int r = w * 16 + rp * 2 + q, a = a0 + r;
+          M[q] = -INFINITY;
+          L[q] = 0.f;
+          aa[q] = a;
+          rok[q] = r < kOwnRows && a < T;
+          pac[q] = AC + static_cast<size_t>(r) * tp;
+          plo[q] = BD + static_cast<size_t>(r) * tp + (T - 1 - a);        // b <= a   : BD[a][T-1-a+b]
+          phi[q] = BD + static_cast<size_t>(r + 1) * tp - (a + 2);        // b >= a+2 : BD[a+1][b-a-2]
+          if (!rok[q]) {   // the loads below are unconditional: a row outside the tile reads (and discards) row 0
+            pac[q] = AC;
+            plo[q] = BD;
+            phi[q] = BD;
           }
         }
-      }
+        if (rok[0]) {   // warp uniform (row 2q+1 may still be outside: its loads are predicated off)
+          for (int c0 = 0; c0 < T; c0 += 256) {
+            // every load is unconditional and in bounds of the scratch (clamped column; the rel-shift pointers of a
+            // row outside the utterance still point into the scratch), so all 32 are in flight before the first use
+            float xv[2][8], yv[2][8], sv[2][8];
 #pragma unroll
-      for (int rr = 0; rr < 16; ++rr) {
-        const float M = warp_max(mrow[rr]);
-        const float part = mrow[rr] > -INFINITY ? lrow[rr] * expf(mrow[rr] - M) : 0.f;
-        const float L = warp_sum(part);
-        mrow[rr] = M;
-        lrow[rr] = L > 0.f ? 1.0f / L : 0.f;   // rows this tile does not own have no scores: probability 0
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int b = min(c0 + 32 * i + lane, T - 1);
+                const float* pb = b <= aa[q] ? plo[q] : phi[q];
+                xv[q][i] = pac[q][b];
+                yv[q][i] = pb[b];
+              }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int b = c0 + 32 * i + lane;
+                const float y = b != aa[q] + 1 ? yv[q][i] : 0.f;
+                sv[q][i] = (rok[q] && b < T) ? (xv[q][i] + y) * sc2 : -INFINITY;
+              }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              float cm = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int b = c0 + 32 * i + lane;
+                if (sv[q][i] > -INFINITY) pac[q][b] = sv[q][i];
+                cm = fmaxf(cm, sv[q][i]);
+              }
+              const float mn = fmaxf(M[q], cm);
+              if (mn > -INFINITY) {
+                float acc = L[q] * ex2_approx(M[q] - mn);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc += ex2_approx(sv[q][i] - mn);
+                L[q] = acc;
+                M[q] = mn;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float Mw = warp_max(M[q]);
+          const float Lw = warp_sum(M[q] > -INFINITY ? L[q] * ex2_approx(M[q] - Mw) : 0.f);
+          mrow[rp * 2 + q] = Lw > 0.f ? Mw : 0.f;          // rows this tile does not own have no scores:
+          lrow[rp * 2 + q] = Lw > 0.f ? 1.0f / Lw : 0.f;   // probability 0 (2^(-inf - 0) * 0)
+        }
       }
       __syncwarp();   // the in-place scores of a row are read below by other lanes of this warp
-      // ---- phase 3: probabilities of 64 keys -> (hi, lo') A-operand chunk (lane = 2 adjacent keys)
-      for (int kc = 0; kc < nkc; ++kc) {
-        const uint32_t pb = pc & 1;
-        mbar_wait(&p_empty[pb], ((pc >> 1) & 1) ^ 1);
-        const int key = kc * 64 + 2 * lane;
-        const uint32_t dst0 = x_addr + pb * kStageB + static_cast<uint32_t>((lane & 3) * 4);
+      if (tr0) ATR(20, it);
+      if (tr4) ATR(26, it);
+      // ---- phase 3: probabilities of 64 keys -> (hi, lo') A-operand chunk (lane = 2 adjacent keys of 16 rows);
+      //      the scores of the next chunk are fetched before this one is converted
+      {
+        float2 cur[16];
+        auto fetch = [&](float2 (&d)[16], int kc) {
+          const int key = kc * 64 + 2 * lane;   // < tp: unconditional loads, masked afterwards
 #pragma unroll
-        for (int rr = 0; rr < 16; ++rr) {
-          const int r = w * 16 + rr;
-          float p0 = 0.f, p1 = 0.f;
-          if (lrow[rr] > 0.f && key < T) {
-            const float2 s2 = *reinterpret_cast<const float2*>(AC + static_cast<size_t>(r) * tp + key);
-            p0 = expf(s2.x - mrow[rr]) * lrow[rr];
-            if (key + 1 < T) p1 = expf(s2.y - mrow[rr]) * lrow[rr];
+          for (int rr = 0; rr < 16; ++rr) d[rr] = *reinterpret_cast<const float2*>(AC + static_cast<size_t>(w * 16 + rr) * tp + key);
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr)
+            if (!(lrow[rr] > 0.f && key < T)) d[rr] = make_float2(-INFINITY, -INFINITY);
+        };
+        fetch(cur, 0);
+        for (int kc = 0; kc < nkc; ++kc) {
+          float2 nxt[16];
+          if (kc + 1 < nkc) fetch(nxt, kc + 1);
+          const uint32_t pb = pc & 1;
+          mbar_wait(&p_empty[pb], ((pc >> 1) & 1) ^ 1);
+          const bool second = kc * 64 + 2 * lane + 1 < T;
+          const uint32_t dst0 = x_addr + pb * kStageB + static_cast<uint32_t>((lane & 3) * 4);
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = w * 16 + rr;
+            const float p0 = ex2_approx(cur[rr].x - mrow[rr]) * lrow[rr];                      // 2^-inf = 0 outside
+            const float p1 = second ? ex2_approx(cur[rr].y - mrow[rr]) * lrow[rr] : 0.f;
+            uint32_t hw, lw;
+            split_pair16(p0, p1, hw, lw);
+            const uint32_t a = dst0 + static_cast<uint32_t>(r * 128) + (static_cast<uint32_t>((lane >> 2) ^ (r & 7)) << 4);
+            sts32(a, hw);
+            sts32(a + kTile16, lw);
           }
-          bf16 h0, l0, h1, l1;
-          split_op16(p0, h0, l0);
-          split_op16(p1, h1, l1);
-          const uint32_t a = dst0 + static_cast<uint32_t>(r * 128) + (static_cast<uint32_t>((lane >> 2) ^ (r & 7)) << 4);
-          sts32(a, pack_f16_bits(h0, h1));
-          sts32(a + kTile16, pack_f16_bits(l0, l1));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[pb]);
+          ++pc;
+          if (kc + 1 < nkc) {
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) cur[rr] = nxt[rr];
+          }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[pb]);
-        ++pc;
       }
-      // ---- context epilogue: TMEM -> (hi, lo') rows of the output projection's operand
-      if (epi) {
+      if (tr0) ATR(21, it);
+      if (tr4) ATR(27, it);
+      // ---- context epilogue: TMEM -> (hi, lo') rows of the output projection's operand; staging row of a thread =
+      //      [16 hi values (32 B) | 16 lo values (32 B)], every warp moves half of the 16-column groups
+      {
         mbar_wait(ctx_full, it & 1);
         tc_fence_after();
-        const int r = quad * 32 + lane, a = a0 + r;
-        const bool valid = r < kOwnRows && a < T;
-        const size_t orow = static_cast<size_t>(ti.seg0 + a) * P.out_ld + ti.h * P.dk;
-        const int nch = P.dk >> 5;
-        for (int ch = 0; ch < nch; ++ch) {
-          uint32_t m[32], c[32];
-          tmem_ld32(lane_base + static_cast<uint32_t>(ch * 32), m);
-          tmem_ld32(lane_base + 256u + static_cast<uint32_t>(ch * 32), c);
+        if (tr0) ATR(22, it);
+        const int n16 = P.dk >> 4, g0 = hsel * (n16 >> 1), g1 = hsel ? n16 : (n16 >> 1);
+        bf16* const obase = (lane & 2) ? P.out_lo : P.out_hi;
+        for (int g = g0; g < g1; ++g) {
+          uint32_t m[16], c[16];
+          tmem_ld16(lane_base + static_cast<uint32_t>(g * 16), m);
+          tmem_ld16(lane_base + 256u + static_cast<uint32_t>(g * 16), c);
           tmem_ld_wait();
-          if (ch == nch - 1) {
+          if (g == g1 - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tile_free);
           }
-          if (valid) {
+          uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t hw[4], lw[4];
+          for (int i = 0; i < 8; ++i)
+            split_pair16(__uint_as_float(m[2 * i]) + __uint_as_float(c[2 * i]) * kInvSplit,
+                         __uint_as_float(m[2 * i + 1]) + __uint_as_float(c[2 * i + 1]) * kInvSplit, hw[i], lw[i]);
+          sts128(stg_w, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          sts128(stg_w + 16, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+          sts128(stg_w + 32, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+          sts128(stg_w + 48, make_uint4(lw[4], lw[5], lw[6], lw[7]));
+          __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                bf16 h0, l0, h1, l1;
-                split_op16(__uint_as_float(m[g * 8 + 2 * i]) + __uint_as_float(c[g * 8 + 2 * i]) * kInvSplit, h0, l0);
-                split_op16(__uint_as_float(m[g * 8 + 2 * i + 1]) + __uint_as_float(c[g * 8 + 2 * i + 1]) * kInvSplit, h1, l1);
-                hw[i] = pack_f16_bits(h0, h1);
-                lw[i] = pack_f16_bits(l0, l1);
-              }
-              *reinterpret_cast<uint4*>(P.out_hi + orow + ch * 32 + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(P.out_lo + orow + ch * 32 + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
+          for (int i = 0; i < 4; ++i) {   // rows 8i .. 8i+7; lanes 0,1 of a row carry hi, lanes 2,3 lo
+            const int r = quad * 32 + i * 8 + (lane >> 2), a = a0 + r;
+            const uint4 v = lds128(stg_r + static_cast<uint32_t>(i * 8 * kStgPitch * 4));
+            if (r < kOwnRows && a < T)
+              *reinterpret_cast<uint4*>(obase + static_cast<size_t>(ti.seg0 + a) * P.out_ld + ti.h * P.dk + g * 16 + (lane & 1) * 8) = v;
           }
+          __syncwarp();
         }
       }
+      if (tr0) ATR(23, it);
       ++it;
     }
   }
@@ -464,6 +584,7 @@ int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const
   P.out_lo = out_lo;
   P.out_ld = out_ld;
   P.scale = 1.0f / sqrtf(static_cast<float>(P.dk));
+  P.trace = g_trace_ptr;
   CUtensorMap mxh, mxl, mvh, mvl, mph, mpl;
   JB_PROPAGATE(make_tmap(&mxh, x_hi, x_rows, 4 * d_model, 4 * d_model, 128));
   JB_PROPAGATE(make_tmap(&mxl, x_lo, x_rows, 4 * d_model, 4 * d_model, 128));
