@@ -12,16 +12,17 @@
 //            (both in TMEM, fp32); accumulation runs in CHAINS of 8 K blocks because tcgen05 truncates when
 //            it adds into TMEM (measured bias 1.7e-5 after 288 MMAs) -- chains ping-pong between
 //            two TMEM buffers
-//   warp 2   epilogue loader: TMA-loads the fp32 residual slabs of upcoming tiles into the epilogue ring
-//   warp 3   store warp: TMA stores of finished slabs (fp32 master and/or fp16 split pair)
 //   warps 4-7 epilogue: drain every chain (tcgen05.ld) and add the partial sums in REGISTERS with
-//            round-to-nearest fp32 (main + corr * 2^-11); after the last chain: bias, ReLU / tanh / GLU,
-//            scale, fp32 residual (from the smem slab), row mask, outputs written in place into the
-//            swizzled smem slabs, fence.proxy.async, mbarrier hand-off to the store warp.
+//            round-to-nearest fp32 (main + corr * 2^-11); after the last chain, 64 columns at a time: bias,
+//            ReLU / tanh / GLU, scale in the thread-per-row domain, then through a per-warp staging tile into
+//            the row-contiguous domain (a ROLLED loop: 2 rows x 16 lanes x 16 B per instruction) where the fp32
+//            residual is added (coalesced loads, prefetched four steps ahead), the row mask applied and the fp32
+//            master and / or fp16 split pair stored with coalesced global stores.
 //
-// The first version of this path (conv_gemm_tc_kernel<128, true>) had the same mainloop but finished
-// tiles with per-thread global loads/stores: measured 52 k clk to store one 128x128 tile against 10-14 k
-// clk of MMA work (tools/gpu_trace1.py).
+// History of the epilogue (tools/gpu_trace_gemm.py): per-thread scattered global stores took 52 k clk per 128x128
+// tile; TMA stores from a ring of swizzled slabs took 11-13 k clk (one store in flight at a time, ~2.9 k clk of
+// store latency per 32-column slab) against 4.6-14 k clk of MMA work per tile, so every GEMM of the model was
+// epilogue bound; the staged coalesced stores need no ring, no store latency and free 48 KB for the weight ring.
 #include <cstdlib>
 
 #include "conv_gemm.cuh"
@@ -40,19 +41,18 @@ constexpr int UK = 16;
 constexpr int kThreads3 = 256;
 constexpr int CHUNK = 8;      // K blocks per accumulation chain
 constexpr int A_STAGES = 2;
-constexpr int MAX_B_STAGES = 6;                // 3 full stages, or 6 half stages when a CTA pair shares the weights
+constexpr int MAX_B_STAGES = 8;                // 4 full stages, or 8 half stages when a CTA pair shares the weights
 constexpr int OP_BYTES = BM * BK * 2;          // 16 KB: one weight tile (hi or lo)
 constexpr int B_STAGE_BYTES = 2 * OP_BYTES;    // B_hi | B_lo
 constexpr int A_SLAB_ROWS = 144;               // 128 + halo of the taps (<= 16 rows)
 constexpr int A_OP_BYTES = A_SLAB_ROWS * BK * 2;   // 18 KB (multiple of 1024)
 constexpr int A_STAGE_BYTES = 2 * A_OP_BYTES;  // A_hi | A_lo
-constexpr int SLAB = 32;                        // columns per epilogue slab
-constexpr int F32_SLAB_BYTES = BM * SLAB * 4;   // 16 KB, 128-byte rows (SWIZZLE_128B)
-constexpr int H16_SLAB_BYTES = BM * SLAB * 2;   // 8 KB, 64-byte rows (SWIZZLE_64B)
-constexpr int MAX_ENTRIES = 6;
+constexpr int HALF = 64;                        // output columns per epilogue pass
+constexpr int STG_PITCH = HALF + 4;             // staging row pitch in words: 64 data + 4 pad (conflict-free 128-bit rows)
+constexpr int STG_BYTES = 32 * STG_PITCH * 4;   // one epilogue warp's [32 rows x 64 words] transpose tile
 constexpr int BIAS_BYTES = 8192;                // n_pad <= 2048
 constexpr int BAR_BYTES = 1024;
-constexpr int SMEM_MISC = BIAS_BYTES + BAR_BYTES + 1024;
+constexpr int SMEM_MISC = BIAS_BYTES + BAR_BYTES + 4 * STG_BYTES + 1024;
 constexpr int smem_fixed(int b_stages) { return A_STAGES * A_STAGE_BYTES + b_stages * B_STAGE_BYTES + SMEM_MISC; }
 constexpr int TMEM_COLS = 512;                  // 2 buffers x (main 128 | corr 128)
 
@@ -66,8 +66,9 @@ struct Params3 {
   const float* bias;
   int act;          // ACT_NONE / ACT_RELU / ACT_TANH / ACT_GLU
   float scale;
-  int has_res, has_f32, has_split;
-  int entries, entry_bytes;
+  const float* res; int res_ld;          // fp32 residual added to the output (may alias out_f32)
+  float* out_f32; int out_f32_ld;        // optional fp32 output
+  bf16* out_hi; bf16* out_lo; int out_h_ld;   // optional fp16 (hi, lo * 2^11) split pair
   int b_stages;     // weight ring depth (2..3)
   int num_groups;   // pair mode: ceil(num_m_tiles / 2) * num_n_tiles (a pair walks 2 M tiles x one N tile at a time)
   int halo_rows;    // rows of the activation slab: 128 + (taps-1)*tap_stride rounded up to 8
@@ -89,42 +90,28 @@ __device__ __forceinline__ uint64_t desc128(uint32_t smem_addr) {  // K-major, 1
   return d;
 }
 
-// number of 32-column output slabs of the tile that starts at GEMM column n0
-__device__ __forceinline__ int tile_slabs(const Params3& P, int n0) {
-  if (P.act == ACT_GLU) {
-    const int o0 = n0 / 2;
-    const int left = P.n - o0;
-    return left >= 64 ? 2 : (left <= 0 ? 0 : (left + SLAB - 1) / SLAB);
-  }
-  const int left = P.n - n0;
-  return left >= BN ? 4 : (left <= 0 ? 0 : (left + SLAB - 1) / SLAB);
-}
-
 // PAIR: the two CTAs of a cluster issue M = 256 cta_group::2 MMAs; each keeps its own 128 activation rows and HALF of
 // every weight tile pair (a template parameter: kernels with cta_group::2 code need an even cluster size to launch)
-template <bool PAIR>
+// ACTK: 0 = none / ReLU (a floor of -inf / 0: one code path), 1 = tanh, 2 = GLU -- a template parameter because the
+// unrolled epilogue with a run-time activation switch compiled to 10 k instructions per kernel (instruction-cache bound)
+template <bool PAIR, int ACTK>
 __global__ void __launch_bounds__(kThreads3, 1)
 gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                      const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_f32,
-                      const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                       const __grid_constant__ Params3 P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_ring = smem + A_STAGES * A_STAGE_BYTES;
   float* bias_s = reinterpret_cast<float*>(b_ring + P.b_stages * B_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + BIAS_BYTES);
-  uint8_t* ep_base = reinterpret_cast<uint8_t*>(bars) + BAR_BYTES;   // 1024-aligned
+  uint8_t* stg_base = reinterpret_cast<uint8_t*>(bars) + BAR_BYTES;   // [4 epilogue warps][STG_BYTES]
   uint64_t* full_bar = bars;                       // [MAX_B_STAGES]  weight ring
   uint64_t* empty_bar = full_bar + MAX_B_STAGES;   // [MAX_B_STAGES]
   uint64_t* afull_bar = empty_bar + MAX_B_STAGES;  // [A_STAGES]      activation slabs
   uint64_t* aempty_bar = afull_bar + A_STAGES;     // [A_STAGES]
   uint64_t* tfull_bar = aempty_bar + A_STAGES;     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-  uint64_t* epfull_bar = tempty_bar + 2;           // [MAX_ENTRIES]
-  uint64_t* epempty_bar = epfull_bar + MAX_ENTRIES;
-  uint64_t* ready_bar = epempty_bar + MAX_ENTRIES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_bar + MAX_ENTRIES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,10 +127,6 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   const int b_depth = PAIR ? 2 * P.b_stages : P.b_stages;
   const int k_iters = P.taps * P.k_chunks;
   const int n_chains = (k_iters + CHUNK - 1) / CHUNK;
-  const int E = P.entries;
-  const int f32_off = 0;
-  const int hi_off = (P.has_res || P.has_f32) ? F32_SLAB_BYTES : 0;
-  const int lo_off = hi_off + H16_SLAB_BYTES;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
@@ -151,11 +134,6 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     for (int i = 0; i < MAX_B_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], PAIR ? 8 : 4); }
-    for (int i = 0; i < MAX_ENTRIES; ++i) {
-      mbar_init(&epfull_bar[i], 1);
-      mbar_init(&epempty_bar[i], 1);
-      mbar_init(&ready_bar[i], 128);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -289,73 +267,17 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         JB_TRACE3(1, 2, seq);
       }
     }
-  } else if (warp == 2) {
-    // ===================== epilogue loader =====================
-    if (elect_one()) {
-      int e = 0;
-      uint32_t ph = 0;
-      for (int u = u0; u < num_units; u += ustep) {
-        const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
-        const int n0 = (u % P.num_n_tiles) * BN;
-        const int ns = tile_slabs(P, n0);
-        const int o0 = P.act == ACT_GLU ? n0 / 2 : n0;
-        for (int s = 0; s < ns; ++s) {
-          mbar_wait(&epempty_bar[e], ph ^ 1);
-          if (P.has_res) {
-            mbar_expect_tx(&epfull_bar[e], F32_SLAB_BYTES);
-            tma_load_2d(&tm_res, &epfull_bar[e], ep_base + e * P.entry_bytes + f32_off, o0 + s * SLAB, m0);
-          } else {
-            mbar_arrive(&epfull_bar[e]);
-          }
-          if (++e == E) { e = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== store warp =====================
-    if (elect_one()) {
-      int e = 0;
-      uint32_t ph = 0;
-      for (int u = u0; u < num_units; u += ustep) {
-        const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
-        const int n0 = (u % P.num_n_tiles) * BN;
-        const int ns = tile_slabs(P, n0);
-        const int o0 = P.act == ACT_GLU ? n0 / 2 : n0;
-        for (int s = 0; s < ns; ++s) {
-          mbar_wait(&ready_bar[e], ph);
-          uint8_t* buf = ep_base + e * P.entry_bytes;
-          if (P.has_f32) tma_store_2d(&tm_f32, buf + f32_off, o0 + s * SLAB, m0);
-          if (P.has_split) {
-            tma_store_2d(&tm_hi, buf + hi_off, o0 + s * SLAB, m0);
-            tma_store_2d(&tm_lo, buf + lo_off, o0 + s * SLAB, m0);
-          }
-          tma_store_commit();
-          tma_store_wait_read<0>();          // smem has been read: the entry can be refilled
-          mbar_arrive(&epempty_bar[e]);
-          if (++e == E) { e = 0; ph ^= 1; }
-        }
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
   } else if (warp >= 4) {
     // ===================== epilogue (warps 4..7) =====================
     const int lane_group = warp & 3;
-    const int row_in_tile = lane_group * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
-    const uint32_t f_row = static_cast<uint32_t>(row_in_tile) * 128u;        // fp32 slab row (128 B)
-    const uint32_t f_sw = static_cast<uint32_t>(row_in_tile) & 7u;
-    const uint32_t h_row = static_cast<uint32_t>(row_in_tile) * 64u;         // fp16 slab row (64 B)
-    const uint32_t h_sw = (h_row >> 7) & 3u;
+    const uint32_t stg = smem_u32(stg_base + (warp - 4) * STG_BYTES);
+    const uint32_t stg_w = stg + static_cast<uint32_t>(lane * STG_PITCH * 4);   // my row of the staging tile
     int buf = 0;
     uint32_t buf_phase = 0;
-    int e = 0;
-    uint32_t ph = 0;
     for (int u = u0, seq = 0; u < num_units; u += ustep, ++seq) {
       const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
       const int n0 = (u % P.num_n_tiles) * BN;
-      const int row = m0 + row_in_tile;
-      unsigned mask_byte = 1u;   // loaded now, compared after the drains (off the critical path)
-      if (row < P.m_rows && P.frame_mask) mask_byte = __ldg(P.frame_mask + row);
       // ---- drain the chains: round-to-nearest fp32 sum of (main + corr * 2^-11) partials
       float accr[BN];
       if (warp == 4 && lane == 0) JB_TRACE3(4, 3, seq);
@@ -383,85 +305,98 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
       }
       if (warp == 4 && lane == 0) JB_TRACE3(4, 0, seq);
-      const bool valid = row < P.m_rows && mask_byte != 0u;
-      const int ns = tile_slabs(P, n0);
-      // ---- finish: one 32-column slab at a time through the epilogue ring
+      // ---- finish: 64 output columns per pass (GLU: the tile's 64 outputs in one pass)
+      const int o0 = ACTK == 2 ? n0 / 2 : n0;
+      const int row0 = m0 + lane_group * 32;
+      // validity of the warp's 32 rows as bit masks: inside the matrix / unmasked (lane = row here)
+      const bool in_me = row0 + lane < P.m_rows;
+      const bool keep_me = in_me && (P.frame_mask == nullptr || __ldg(P.frame_mask + row0 + lane) != 0);
+      const uint32_t inbits = __ballot_sync(0xffffffffu, in_me), keepbits = __ballot_sync(0xffffffffu, keep_me);
+      const float act_floor = P.act == ACT_RELU ? 0.f : -INFINITY;
+      const uint32_t bias_addr = smem_u32(bias_s);
+      const int c4 = (lane & 15) * 4;     // this lane's 4 columns of a pass in the row-contiguous domain
+      const int rsub = lane >> 4;         // which of the two rows of a step
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        if (s < ns) {
-          mbar_wait(&epfull_bar[e], ph);
-          uint8_t* ebuf = ep_base + e * P.entry_bytes;
-          float v[32];
-          const uint32_t bias_addr = smem_u32(bias_s);
-          auto bias32 = [&](int col0, float (&b)[32]) {   // 32 consecutive bias values by shared-space 128-bit loads
+      for (int h = 0; h < (ACTK == 2 ? 1 : 2); ++h) {
+        const int ocol0 = o0 + h * HALF;
+        if (ocol0 >= P.n) break;
+        // ---- thread = row: bias, activation, scale; 16 x 128-bit stores into my staging row
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const uint4 t = lds128(bias_addr + static_cast<uint32_t>(col0 + 4 * q) * 4u);
-              b[4 * q] = __uint_as_float(t.x); b[4 * q + 1] = __uint_as_float(t.y);
-              b[4 * q + 2] = __uint_as_float(t.z); b[4 * q + 3] = __uint_as_float(t.w);
-            }
-          };
-          if (P.act == ACT_GLU) {
+        for (int q = 0; q < 16; ++q) {
+          float v[4];
+          if constexpr (ACTK == 2) {
             // tile columns [0,64) linear half, [64,128) gate half of the same 64 output channels
-            float ba[32], bg[32];
-            bias32(n0 + (s & 1) * 32, ba);
-            bias32(n0 + 64 + (s & 1) * 32, bg);
+            const uint4 ba = lds128(bias_addr + static_cast<uint32_t>(n0 + 4 * q) * 4u);
+            const uint4 bg = lds128(bias_addr + static_cast<uint32_t>(n0 + 64 + 4 * q) * 4u);
+            const float bav[4] = {__uint_as_float(ba.x), __uint_as_float(ba.y), __uint_as_float(ba.z), __uint_as_float(ba.w)};
+            const float bgv[4] = {__uint_as_float(bg.x), __uint_as_float(bg.y), __uint_as_float(bg.z), __uint_as_float(bg.w)};
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int ca = (s & 1) * 32 + i;   // s < 2 in GLU mode
-              const float a = accr[ca] + ba[i];
-              const float g = accr[64 + ca] + bg[i];
-              v[i] = a * (1.0f / (1.0f + __expf(-g))) * P.scale;
+            for (int i = 0; i < 4; ++i) {
+              const float a = accr[4 * q + i] + bav[i];
+              const float gt = accr[64 + 4 * q + i] + bgv[i];
+              v[i] = a * (1.0f / (1.0f + __expf(-gt))) * P.scale;
             }
           } else {
-            float bb[32];
-            bias32(n0 + s * 32, bb);
+            const uint4 bb = lds128(bias_addr + static_cast<uint32_t>(n0 + h * HALF + 4 * q) * 4u);
+            const float bv[4] = {__uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = accr[s * 32 + i] + bb[i];
-              if (P.act == ACT_RELU) x = fmaxf(x, 0.f);
-              else if (P.act == ACT_TANH) x = tanhf(x);
+            for (int i = 0; i < 4; ++i) {
+              float x = accr[h * HALF + 4 * q + i] + bv[i];
+              if constexpr (ACTK == 1) x = tanhf(x);
+              else x = fmaxf(x, act_floor);
               v[i] = x * P.scale;
             }
           }
-          if (P.has_res || P.has_f32) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {   // 8 chunks of 4 floats
-              const uint32_t off = f_row + ((static_cast<uint32_t>(c) ^ f_sw) << 4);
-              float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-              if (P.has_res) {
-                const uint4 ru = lds128(smem_u32(ebuf) + f32_off + off);
-                const float4 r4 = make_float4(__uint_as_float(ru.x), __uint_as_float(ru.y), __uint_as_float(ru.z), __uint_as_float(ru.w));
-                o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-                v[4 * c] = o.x; v[4 * c + 1] = o.y; v[4 * c + 2] = o.z; v[4 * c + 3] = o.w;
-              }
-              if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (P.has_f32)
-                sts128(smem_u32(ebuf) + f32_off + off, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
-            }
-          }
-          if (P.has_split) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {   // 4 chunks of 8 halves
-              const uint32_t off = h_row + ((static_cast<uint32_t>(c) ^ h_sw) << 4);
-              uint32_t ph4[4], pl4[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                bf16 ah, al, bh, bl;
-                split_op16(valid ? v[8 * c + 2 * j] : 0.f, ah, al);
-                split_op16(valid ? v[8 * c + 2 * j + 1] : 0.f, bh, bl);
-                __nv_bfloat162 hh = __halves2bfloat162(ah, bh), ll = __halves2bfloat162(al, bl);
-                ph4[j] = *reinterpret_cast<uint32_t*>(&hh);
-                pl4[j] = *reinterpret_cast<uint32_t*>(&ll);
-              }
-              sts128(smem_u32(ebuf) + hi_off + off, make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]));
-              sts128(smem_u32(ebuf) + lo_off + off, make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]));
-            }
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(&ready_bar[e]);
-          if (++e == E) { e = 0; ph ^= 1; }
+          sts128(stg_w + static_cast<uint32_t>(q * 16), make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]),
+                                                                    __float_as_uint(v[2]), __float_as_uint(v[3])));
         }
+        __syncwarp();
+        // ---- lanes along the columns: 16 steps of 2 rows; residual rows are fetched one block of 4 steps ahead
+        const int col = ocol0 + c4;
+        const bool col_ok = col < P.n;
+        auto fetch_res = [&](float4 (&d)[4], int blk) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = (blk * 4 + i) * 2 + rsub;
+            d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (P.res != nullptr && col_ok && ((inbits >> rl) & 1u))
+              d[i] = *reinterpret_cast<const float4*>(P.res + static_cast<long long>(row0 + rl) * P.res_ld + col);
+          }
+        };
+        float4 rcur[4];
+        fetch_res(rcur, 0);
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) {
+          float4 rnxt[4];
+          if (blk + 1 < 4) fetch_res(rnxt, blk + 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = (blk * 4 + i) * 2 + rsub;
+            const uint4 t = lds128(stg + static_cast<uint32_t>((rl * STG_PITCH + c4) * 4));
+            float4 o = make_float4(__uint_as_float(t.x) + rcur[i].x, __uint_as_float(t.y) + rcur[i].y,
+                                   __uint_as_float(t.z) + rcur[i].z, __uint_as_float(t.w) + rcur[i].w);
+            if (!((keepbits >> rl) & 1u)) o = make_float4(0.f, 0.f, 0.f, 0.f);   // masked rows are stored as zeros
+            if (col_ok && ((inbits >> rl) & 1u)) {
+              const long long row = row0 + rl;
+              if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col) = o;
+              if (P.out_hi) {
+                bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+                split_op16(o.x, h0, l0); split_op16(o.y, h1, l1); split_op16(o.z, h2, l2); split_op16(o.w, h3, l3);
+                const __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
+                const __nv_bfloat162 la = __halves2bfloat162(l0, l1), lb = __halves2bfloat162(l2, l3);
+                *reinterpret_cast<uint2*>(P.out_hi + row * P.out_h_ld + col) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+                *reinterpret_cast<uint2*>(P.out_lo + row * P.out_h_ld + col) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+              }
+            }
+          }
+          if (blk + 1 < 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
+          }
+        }
+        __syncwarp();
       }
       if (warp == 4 && lane == 0) JB_TRACE3(4, 2, seq);
     }
@@ -483,22 +418,6 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   }
 }
 
-// 2-D fp32 row-major [rows, ld] matrix, box = [128 rows, 32 cols] (128-byte rows), 128B swizzle
-int make_tmap_f32(CUtensorMap* map, const float* base, long long rows, int cols, int ld) {
-  EncodeTiledFn fn = get_encode_fn();
-  JB_REQUIRE(fn != nullptr, -3, "cuTensorMapEncodeTiled entry point not available");
-  JB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 4) % 16 == 0, -2, "fp32 TMA alignment");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {SLAB, BM};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  JB_REQUIRE(r == CUDA_SUCCESS, -3, "cuTensorMapEncodeTiled(fp32) failed (code " + std::to_string(static_cast<int>(r)) + ")");
-  return 0;
-}
-
 }  // namespace
 
 bool conv_gemm_tc3_eligible(const ConvGemmProblem& p) {
@@ -512,6 +431,7 @@ bool conv_gemm_tc3_eligible(const ConvGemmProblem& p) {
   if (p.rate > 1) return false;
   if (p.tap_stride < 0 || (p.taps - 1) * p.tap_stride > A_SLAB_ROWS - BM) return false;
   if (e.act == ACT_GLU && (e.out_hi || e.res_f32)) return false;
+  if (p.n % 4 != 0) return false;   // the epilogue stores 4 columns per lane
   auto f32_ok = [&](const float* ptr, int ld) { return ptr == nullptr || (ld % 4 == 0 && ld >= p.n && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0); };
   auto h_ok = [&](const bf16* ptr, int ld) { return ptr == nullptr || (ld % 8 == 0 && ld >= p.n && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0); };
   if (!f32_ok(e.res_f32, e.res_ld) || !f32_ok(e.out_f32, e.out_f32_ld) || !h_ok(e.out_hi, e.out_bf_ld) || !h_ok(e.out_lo, e.out_bf_ld))
@@ -521,7 +441,7 @@ bool conv_gemm_tc3_eligible(const ConvGemmProblem& p) {
 
 int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   const ConvGemmEpilogue& e = p.ep;
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const int a_cols = p.a_cols > 0 ? p.a_cols : p.k_pad;
   const int halo_rows = round_up(BM + (p.taps - 1) * p.tap_stride, 8);
   JB_PROPAGATE(make_tmap(&ta_hi, p.a_hi, p.a_rows, a_cols, p.a_ld, halo_rows));
@@ -532,13 +452,6 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   const bool pair = env_pair != 0 && ceil_div(p.m_rows, BM) >= 4;
   JB_PROPAGATE(make_tmap(&tb_hi, p.w_hi, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, pair ? BN / 2 : BN));
   JB_PROPAGATE(make_tmap(&tb_lo, p.w_lo, static_cast<long long>(p.taps) * p.n_pad, p.k_pad, p.k_pad, pair ? BN / 2 : BN));
-  tres = tf32 = thi = tlo = ta_hi;
-  if (e.res_f32) JB_PROPAGATE(make_tmap_f32(&tres, e.res_f32, p.m_rows, p.n, e.res_ld));
-  if (e.out_f32) JB_PROPAGATE(make_tmap_f32(&tf32, e.out_f32, p.m_rows, p.n, e.out_f32_ld));
-  if (e.out_hi) {
-    JB_PROPAGATE(make_tmap(&thi, e.out_hi, p.m_rows, p.n, e.out_bf_ld, BM, SLAB));
-    JB_PROPAGATE(make_tmap(&tlo, e.out_lo, p.m_rows, p.n, e.out_bf_ld, BM, SLAB));
-  }
   Params3 kp;
   kp.taps = p.taps;
   kp.k_chunks = ceil_div(a_cols, BK);
@@ -554,22 +467,24 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.bias = e.bias;
   kp.act = e.act;
   kp.scale = e.scale;
-  kp.has_res = e.res_f32 != nullptr;
-  kp.has_f32 = e.out_f32 != nullptr;
-  kp.has_split = e.out_hi != nullptr;
-  kp.entry_bytes = ((kp.has_res || kp.has_f32) ? F32_SLAB_BYTES : 0) + (kp.has_split ? 2 * H16_SLAB_BYTES : 0);
+  kp.res = e.res_f32; kp.res_ld = e.res_ld;
+  kp.out_f32 = e.out_f32; kp.out_f32_ld = e.out_f32_ld;
+  kp.out_hi = e.out_hi; kp.out_lo = e.out_lo; kp.out_h_ld = e.out_bf_ld;
   kp.halo_rows = halo_rows;
-  // three weight stages when the epilogue ring still gets three entries, else two
-  kp.b_stages = (227 * 1024 - smem_fixed(3)) / kp.entry_bytes >= 3 ? 3 : 2;
-  const int SMEM_FIXED = smem_fixed(kp.b_stages);
-  int entries = (227 * 1024 - SMEM_FIXED) / kp.entry_bytes;
-  if (entries > MAX_ENTRIES) entries = MAX_ENTRIES;
-  JB_REQUIRE(entries >= 2, -2, "conv_gemm_tc3: shared memory budget exceeded");
-  kp.entries = entries;
+  // the weight ring takes what the activation slabs, bias table and staging tiles leave: 3 stages (6 half stages per
+  // CTA in pair mode)
+  kp.b_stages = (227 * 1024 - smem_fixed(0)) / B_STAGE_BYTES;
+  if (kp.b_stages > MAX_B_STAGES / 2) kp.b_stages = MAX_B_STAGES / 2;
+  JB_REQUIRE(kp.b_stages >= 2, -2, "conv_gemm_tc3: shared memory budget exceeded");
   kp.trace = g_trace_ptr;
-  const int smem_bytes = SMEM_FIXED + entries * kp.entry_bytes;
-  JB_PROPAGATE(ensure_dynamic_smem(pair ? reinterpret_cast<const void*>(gemm_split_tma_kernel<true>)
-                                        : reinterpret_cast<const void*>(gemm_split_tma_kernel<false>), smem_bytes));
+  const int smem_bytes = smem_fixed(kp.b_stages);
+  const int actk = e.act == ACT_GLU ? 2 : (e.act == ACT_TANH ? 1 : 0);
+  using KernFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params3);
+  static const KernFn kerns[2][3] = {
+      {gemm_split_tma_kernel<false, 0>, gemm_split_tma_kernel<false, 1>, gemm_split_tma_kernel<false, 2>},
+      {gemm_split_tma_kernel<true, 0>, gemm_split_tma_kernel<true, 1>, gemm_split_tma_kernel<true, 2>}};
+  const KernFn kern = kerns[pair ? 1 : 0][actk];
+  JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_bytes));
   const int units = pair ? kp.num_groups : kp.num_m_tiles * kp.num_n_tiles;
   if (units == 0) return 0;
   const int max_units = pair ? num_sms() / 2 : num_sms();
@@ -580,10 +495,7 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  if (!pair)
-    JB_CUDA_OK(launch_tc(gemm_split_tma_kernel<false>, grid, kThreads3, smem_bytes, stream, 1, ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp));
-  else
-    JB_CUDA_OK(launch_tc(gemm_split_tma_kernel<true>, grid, kThreads3, smem_bytes, stream, 2, ta_hi, ta_lo, tb_hi, tb_lo, tres, tf32, thi, tlo, kp));
+  JB_CUDA_OK(launch_tc(kern, grid, kThreads3, smem_bytes, stream, pair ? 2 : 1, ta_hi, ta_lo, tb_hi, tb_lo, kp));
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));
