@@ -94,6 +94,17 @@ __device__ __forceinline__ void split_op16(float x, bf16& hi, bf16& lo) {
   hi = *reinterpret_cast<const bf16*>(&h);
   lo = *reinterpret_cast<const bf16*>(&l);
 }
+// Two values at once with the packed conversions (one F2FP per pair instead of three scalar F2F per value, which run
+// at a quarter of the ALU rate): returns the packed (hi, hi) and (lo', lo') fp16 words; saturates like split_op16.
+__device__ __forceinline__ void split_pair16_sat(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = a > 65504.f ? 65504.f : (a < -65504.f ? -65504.f : a);   // comparisons, not fmin / fmax: NaN propagates
+  b = b > 65504.f ? 65504.f : (b < -65504.f ? -65504.f : b);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * kSplitScale, (b - hf.y) * kSplitScale);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -50,9 +50,12 @@ constexpr int A_STAGE_BYTES = 2 * A_OP_BYTES;  // A_hi | A_lo
 constexpr int HALF = 64;                        // output columns per epilogue pass
 constexpr int STG_PITCH = HALF + 4;             // staging row pitch in words: 64 data + 4 pad (conflict-free 128-bit rows)
 constexpr int STG_BYTES = 32 * STG_PITCH * 4;   // one epilogue warp's [32 rows x 64 words] transpose tile
+constexpr int STG1_PITCH = 32 + 4;              // single-chain kernels: 8 epilogue warps, 32-column passes
+constexpr int STG1_BYTES = 32 * STG1_PITCH * 4;
+constexpr int STG_TOTAL = 8 * STG1_BYTES > 4 * STG_BYTES ? 8 * STG1_BYTES : 4 * STG_BYTES;
 constexpr int BIAS_BYTES = 8192;                // n_pad <= 2048
 constexpr int BAR_BYTES = 1024;
-constexpr int SMEM_MISC = BIAS_BYTES + BAR_BYTES + 4 * STG_BYTES + 1024;
+constexpr int SMEM_MISC = BIAS_BYTES + BAR_BYTES + STG_TOTAL + 1024;
 constexpr int smem_fixed(int b_stages) { return A_STAGES * A_STAGE_BYTES + b_stages * B_STAGE_BYTES + SMEM_MISC; }
 constexpr int TMEM_COLS = 512;                  // 2 buffers x (main 128 | corr 128)
 
@@ -72,6 +75,8 @@ struct Params3 {
   int b_stages;     // weight ring depth (2..3)
   int num_groups;   // pair mode: ceil(num_m_tiles / 2) * num_n_tiles (a pair walks 2 M tiles x one N tile at a time)
   int halo_rows;    // rows of the activation slab: 128 + (taps-1)*tap_stride rounded up to 8
+  int dbg;          // debug (JATTS_B200_TC3_DEBUG, results are WRONG): 1 = no global stores, 2 = no row-contiguous pass at all,
+                    // 3 = also no staging stores; isolates what bounds the epilogue in the per-role timelines
   long long* trace;
 };
 
@@ -90,12 +95,72 @@ __device__ __forceinline__ uint64_t desc128(uint32_t smem_addr) {  // K-major, 1
   return d;
 }
 
+// Row-contiguous half of an epilogue pass: the warp's staging tile holds [32 rows x COLS] finished fp32 values
+// (pitch words per row); COLS/4 lanes x 16 B cover one row, so a step stores 128 / COLS rows.  The fp32 residual is added
+// here (coalesced loads, fetched one block of 4 steps ahead), masked rows become zeros, and the fp32 master and / or the
+// fp16 (hi, lo * 2^11) pair are written with coalesced global stores.
+template <int COLS>
+__device__ __forceinline__ void store_pass(const Params3& P, uint32_t stg, int pitch, int row0, int ocol0, uint32_t inbits,
+                                           uint32_t keepbits, int lane) {
+  constexpr int LPR = COLS / 4;        // lanes per row
+  constexpr int RPS = 32 / LPR;        // rows per step
+  constexpr int STEPS = 32 / RPS;
+  const int c4 = (lane % LPR) * 4;
+  const int rsub = lane / LPR;
+  const int col = ocol0 + c4;
+  const bool col_ok = col < P.n;
+  auto fetch_res = [&](float4 (&d)[4], int blk) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = (blk * 4 + i) * RPS + rsub;
+      d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (P.res != nullptr && col_ok && ((inbits >> rl) & 1u))
+        d[i] = *reinterpret_cast<const float4*>(P.res + static_cast<long long>(row0 + rl) * P.res_ld + col);
+    }
+  };
+  if (P.dbg >= 2) return;
+  float4 rcur[4];
+  fetch_res(rcur, 0);
+#pragma unroll 1
+  for (int blk = 0; blk < STEPS / 4; ++blk) {
+    float4 rnxt[4];
+    if (blk + 1 < STEPS / 4) fetch_res(rnxt, blk + 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = (blk * 4 + i) * RPS + rsub;
+      const uint4 t = lds128(stg + static_cast<uint32_t>((rl * pitch + c4) * 4));
+      float4 o = make_float4(__uint_as_float(t.x) + rcur[i].x, __uint_as_float(t.y) + rcur[i].y,
+                             __uint_as_float(t.z) + rcur[i].z, __uint_as_float(t.w) + rcur[i].w);
+      if (!((keepbits >> rl) & 1u)) o = make_float4(0.f, 0.f, 0.f, 0.f);   // masked rows are stored as zeros
+      if (col_ok && ((inbits >> rl) & 1u) && P.dbg == 0) {
+        const long long row = row0 + rl;
+        if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col) = o;
+        if (P.out_hi) {
+          uint32_t ha, la, hb, lb;
+          split_pair16_sat(o.x, o.y, ha, la);
+          split_pair16_sat(o.z, o.w, hb, lb);
+          *reinterpret_cast<uint2*>(P.out_hi + row * P.out_h_ld + col) = make_uint2(ha, hb);
+          *reinterpret_cast<uint2*>(P.out_lo + row * P.out_h_ld + col) = make_uint2(la, lb);
+        }
+      }
+    }
+    if (blk + 1 < STEPS / 4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
+    }
+  }
+}
+
 // PAIR: the two CTAs of a cluster issue M = 256 cta_group::2 MMAs; each keeps its own 128 activation rows and HALF of
 // every weight tile pair (a template parameter: kernels with cta_group::2 code need an even cluster size to launch)
 // ACTK: 0 = none / ReLU (a floor of -inf / 0: one code path), 1 = tanh, 2 = GLU -- a template parameter because the
 // unrolled epilogue with a run-time activation switch compiled to 10 k instructions per kernel (instruction-cache bound)
-template <bool PAIR, int ACTK>
-__global__ void __launch_bounds__(kThreads3, 1)
+// SINGLE: every tile is one accumulation chain (K <= 8 blocks: the projections and pointwise convolutions, 4.6 k clk of
+// MMAs per tile).  Four epilogue warps issue one dependent instruction stream per scheduler and need 11-12 k clk per
+// tile (tools/gpu_trace_gemm.py), so these launches run TWO epilogue groups (12 warps), one per TMEM buffer, that
+// read the accumulators straight into the staging tiles (no register copy of the tile, so 384 threads fit).
+template <bool PAIR, int ACTK, bool SINGLE>
+__global__ void __launch_bounds__(SINGLE ? 384 : kThreads3, 1)
 gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                       const __grid_constant__ Params3 P) {
@@ -151,7 +216,7 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   }
   {
     const int n_bias = P.act == ACT_GLU ? 2 * P.n : P.n;   // entries the bias tensor really has
-    for (int i = threadIdx.x; i < P.n_pad && i < BIAS_BYTES / 4; i += kThreads3)
+    for (int i = threadIdx.x; i < P.n_pad && i < BIAS_BYTES / 4; i += blockDim.x)
       bias_s[i] = (P.bias && i < n_bias) ? P.bias[i] : 0.f;
   }
   tc_fence_before();
@@ -267,6 +332,88 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         JB_TRACE3(1, 2, seq);
       }
     }
+  } else if (warp >= 4 && SINGLE) {
+    // ===================== epilogue, single-chain tiles: group e = (warp - 4) / 4 owns TMEM buffer e =====================
+    const int lane_group = warp & 3;
+    const int e = (warp - 4) >> 2;
+    const uint32_t tb = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + static_cast<uint32_t>(e * 2 * BN);
+    const uint32_t stg = smem_u32(stg_base + (warp - 4) * STG1_BYTES);
+    const uint32_t stg_w = stg + static_cast<uint32_t>(lane * STG1_PITCH * 4);
+    const float act_floor = P.act == ACT_RELU ? 0.f : -INFINITY;
+    const uint32_t bias_addr = smem_u32(bias_s);
+    constexpr int NPASS = ACTK == 2 ? 2 : 4;
+    uint32_t ph = 0;
+    for (int u = u0 + e * ustep, seq = e; u < num_units; u += 2 * ustep, seq += 2) {
+      const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
+      const int n0 = (u % P.num_n_tiles) * BN;
+      const int o0 = ACTK == 2 ? n0 / 2 : n0;
+      const int row0 = m0 + lane_group * 32;
+      const bool in_me = row0 + lane < P.m_rows;
+      const bool keep_me = in_me && (P.frame_mask == nullptr || __ldg(P.frame_mask + row0 + lane) != 0);
+      const uint32_t inbits = __ballot_sync(0xffffffffu, in_me), keepbits = __ballot_sync(0xffffffffu, keep_me);
+      if (warp == 4 && lane == 0) JB_TRACE3(4, 3, seq);
+      mbar_wait(&tfull_bar[e], ph);
+      ph ^= 1;
+      tc_fence_after();
+      if (warp == 4 && lane == 0) JB_TRACE3(4, 0, seq);
+#pragma unroll 1
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int ocol0 = o0 + ps * 32;
+        const bool last = ps == NPASS - 1 || ocol0 + 32 >= P.n;
+        // ---- thread = row: 32 columns of the accumulator pair -> bias, activation, scale -> my staging row
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int tc = ps * 32 + hf * 16;   // tile column of this group (GLU: linear half; the gate is 64 further)
+          uint32_t m[16], c[16], mg[16], cg[16];
+          tmem_ld16(tb + static_cast<uint32_t>(tc), m);
+          tmem_ld16(tb + static_cast<uint32_t>(BN + tc), c);
+          if constexpr (ACTK == 2) {
+            tmem_ld16(tb + static_cast<uint32_t>(64 + tc), mg);
+            tmem_ld16(tb + static_cast<uint32_t>(BN + 64 + tc), cg);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 bb = lds128(bias_addr + static_cast<uint32_t>(n0 + tc + 4 * q) * 4u);
+            const float bv[4] = {__uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
+            float v[4];
+            if constexpr (ACTK == 2) {
+              const uint4 bg = lds128(bias_addr + static_cast<uint32_t>(n0 + 64 + tc + 4 * q) * 4u);
+              const float gv[4] = {__uint_as_float(bg.x), __uint_as_float(bg.y), __uint_as_float(bg.z), __uint_as_float(bg.w)};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float a = fmaf(__uint_as_float(c[4 * q + i]), 1.0f / kSplitScale, __uint_as_float(m[4 * q + i])) + bv[i];
+                const float gt = fmaf(__uint_as_float(cg[4 * q + i]), 1.0f / kSplitScale, __uint_as_float(mg[4 * q + i])) + gv[i];
+                v[i] = a * (1.0f / (1.0f + __expf(-gt))) * P.scale;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float x = fmaf(__uint_as_float(c[4 * q + i]), 1.0f / kSplitScale, __uint_as_float(m[4 * q + i])) + bv[i];
+                if constexpr (ACTK == 1) x = tanhf(x);
+                else x = fmaxf(x, act_floor);
+                v[i] = x * P.scale;
+              }
+            }
+            if (P.dbg < 3) sts128(stg_w + static_cast<uint32_t>((hf * 16 + 4 * q) * 4), make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]),
+                                                                                     __float_as_uint(v[2]), __float_as_uint(v[3])));
+          }
+        }
+        if (last) {   // the accumulators of this tile have been read: hand the buffer back to the MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[e]), 0));
+            else mbar_arrive(&tempty_bar[e]);
+          }
+        }
+        __syncwarp();
+        store_pass<32>(P, stg, STG1_PITCH, row0, ocol0, inbits, keepbits, lane);
+        __syncwarp();
+        if (last) break;
+      }
+      if (warp == 4 && lane == 0) JB_TRACE3(4, 2, seq);
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (warps 4..7) =====================
     const int lane_group = warp & 3;
@@ -278,9 +425,9 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     for (int u = u0, seq = 0; u < num_units; u += ustep, ++seq) {
       const int m0 = ((u / P.num_n_tiles) * CL + rank) * BM;
       const int n0 = (u % P.num_n_tiles) * BN;
+      if (warp == 4 && lane == 0) JB_TRACE3(4, 3, seq);
       // ---- drain the chains: round-to-nearest fp32 sum of (main + corr * 2^-11) partials
       float accr[BN];
-      if (warp == 4 && lane == 0) JB_TRACE3(4, 3, seq);
       for (int ch = 0; ch < n_chains; ++ch) {
         mbar_wait(&tfull_bar[buf], buf_phase);
         tc_fence_after();
@@ -314,8 +461,6 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       const uint32_t inbits = __ballot_sync(0xffffffffu, in_me), keepbits = __ballot_sync(0xffffffffu, keep_me);
       const float act_floor = P.act == ACT_RELU ? 0.f : -INFINITY;
       const uint32_t bias_addr = smem_u32(bias_s);
-      const int c4 = (lane & 15) * 4;     // this lane's 4 columns of a pass in the row-contiguous domain
-      const int rsub = lane >> 4;         // which of the two rows of a step
 #pragma unroll
       for (int h = 0; h < (ACTK == 2 ? 1 : 2); ++h) {
         const int ocol0 = o0 + h * HALF;
@@ -351,51 +496,7 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                                                                     __float_as_uint(v[2]), __float_as_uint(v[3])));
         }
         __syncwarp();
-        // ---- lanes along the columns: 16 steps of 2 rows; residual rows are fetched one block of 4 steps ahead
-        const int col = ocol0 + c4;
-        const bool col_ok = col < P.n;
-        auto fetch_res = [&](float4 (&d)[4], int blk) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rl = (blk * 4 + i) * 2 + rsub;
-            d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (P.res != nullptr && col_ok && ((inbits >> rl) & 1u))
-              d[i] = *reinterpret_cast<const float4*>(P.res + static_cast<long long>(row0 + rl) * P.res_ld + col);
-          }
-        };
-        float4 rcur[4];
-        fetch_res(rcur, 0);
-#pragma unroll 1
-        for (int blk = 0; blk < 4; ++blk) {
-          float4 rnxt[4];
-          if (blk + 1 < 4) fetch_res(rnxt, blk + 1);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rl = (blk * 4 + i) * 2 + rsub;
-            const uint4 t = lds128(stg + static_cast<uint32_t>((rl * STG_PITCH + c4) * 4));
-            float4 o = make_float4(__uint_as_float(t.x) + rcur[i].x, __uint_as_float(t.y) + rcur[i].y,
-                                   __uint_as_float(t.z) + rcur[i].z, __uint_as_float(t.w) + rcur[i].w);
-            if (!((keepbits >> rl) & 1u)) o = make_float4(0.f, 0.f, 0.f, 0.f);   // masked rows are stored as zeros
-            if (col_ok && ((inbits >> rl) & 1u)) {
-              const long long row = row0 + rl;
-              if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + row * P.out_f32_ld + col) = o;
-              if (P.out_hi) {
-                bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-                split_op16(o.x, h0, l0); split_op16(o.y, h1, l1); split_op16(o.z, h2, l2); split_op16(o.w, h3, l3);
-                const __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
-                const __nv_bfloat162 la = __halves2bfloat162(l0, l1), lb = __halves2bfloat162(l2, l3);
-                *reinterpret_cast<uint2*>(P.out_hi + row * P.out_h_ld + col) =
-                    make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
-                *reinterpret_cast<uint2*>(P.out_lo + row * P.out_h_ld + col) =
-                    make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
-              }
-            }
-          }
-          if (blk + 1 < 4) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
-          }
-        }
+        store_pass<HALF>(P, stg, STG_PITCH, row0, ocol0, inbits, keepbits, lane);
         __syncwarp();
       }
       if (warp == 4 && lane == 0) JB_TRACE3(4, 2, seq);
@@ -477,13 +578,19 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   if (kp.b_stages > MAX_B_STAGES / 2) kp.b_stages = MAX_B_STAGES / 2;
   JB_REQUIRE(kp.b_stages >= 2, -2, "conv_gemm_tc3: shared memory budget exceeded");
   kp.trace = g_trace_ptr;
+  static const int env_dbg = getenv("JATTS_B200_TC3_DEBUG") ? atoi(getenv("JATTS_B200_TC3_DEBUG")) : 0;
+  kp.dbg = env_dbg;
   const int smem_bytes = smem_fixed(kp.b_stages);
   const int actk = e.act == ACT_GLU ? 2 : (e.act == ACT_TANH ? 1 : 0);
+  // single-chain launches (K <= 8 blocks) run the 12-warp kernel with two epilogue groups
+  const int single = kp.taps * kp.k_chunks <= CHUNK ? 1 : 0;
   using KernFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params3);
-  static const KernFn kerns[2][3] = {
-      {gemm_split_tma_kernel<false, 0>, gemm_split_tma_kernel<false, 1>, gemm_split_tma_kernel<false, 2>},
-      {gemm_split_tma_kernel<true, 0>, gemm_split_tma_kernel<true, 1>, gemm_split_tma_kernel<true, 2>}};
-  const KernFn kern = kerns[pair ? 1 : 0][actk];
+  static const KernFn kerns[2][2][3] = {
+      {{gemm_split_tma_kernel<false, 0, false>, gemm_split_tma_kernel<false, 1, false>, gemm_split_tma_kernel<false, 2, false>},
+       {gemm_split_tma_kernel<true, 0, false>, gemm_split_tma_kernel<true, 1, false>, gemm_split_tma_kernel<true, 2, false>}},
+      {{gemm_split_tma_kernel<false, 0, true>, gemm_split_tma_kernel<false, 1, true>, gemm_split_tma_kernel<false, 2, true>},
+       {gemm_split_tma_kernel<true, 0, true>, gemm_split_tma_kernel<true, 1, true>, gemm_split_tma_kernel<true, 2, true>}}};
+  const KernFn kern = kerns[single][pair ? 1 : 0][actk];
   JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_bytes));
   const int units = pair ? kp.num_groups : kp.num_m_tiles * kp.num_n_tiles;
   if (units == 0) return 0;
@@ -495,7 +602,7 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  JB_CUDA_OK(launch_tc(kern, grid, kThreads3, smem_bytes, stream, pair ? 2 : 1, ta_hi, ta_lo, tb_hi, tb_lo, kp));
+  JB_CUDA_OK(launch_tc(kern, grid, single ? 384 : kThreads3, smem_bytes, stream, pair ? 2 : 1, ta_hi, ta_lo, tb_hi, tb_lo, kp));
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));
