@@ -68,6 +68,11 @@ JATTS_API int64_t jatts_launch_count(void);
 JATTS_API int jatts_profile_begin(void);
 JATTS_API int jatts_profile_end(double* ms_bf16, int64_t* n_bf16, double* ms_split, int64_t* n_split);
 
+/* Same, per kernel class: ms[c] / n[c] for c = 0 bf16 convolutions, 1 split GEMMs, 2 attention, 3 LayerNorm (incl. the
+ * predictors' LayerNorm + Linear tails), 4 depthwise conv + Swish, 5 length regulator, 6 output conv + tanh.
+ * n_classes >= 7. */
+JATTS_API int jatts_profile_end_classes(double* ms, int64_t* n, int32_t n_classes);
+
 /* debug: per-role clock64 timeline of CTA 0 of the TMA-epilogue convolution kernel (d_buf: 5*8*64 int64, or NULL) */
 JATTS_API int jatts_debug_set_trace(void* d_buf);
 

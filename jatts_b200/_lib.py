@@ -83,7 +83,7 @@ EXPORTS = (
     "jatts_fs2_create", "jatts_fs2_destroy", "jatts_fs2_plan", "jatts_fs2_run",
     "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_hifigan_run_pcm16", "jatts_op_conv_gemm", "jatts_op_mrf_pair",
     "jatts_op_relpos_attention",
-    "jatts_profile_begin", "jatts_profile_end", "jatts_debug_set_trace",
+    "jatts_profile_begin", "jatts_profile_end", "jatts_profile_end_classes", "jatts_debug_set_trace",
 )
 
 
@@ -114,6 +114,7 @@ def _load():
     lib.jatts_op_mrf_pair.argtypes = [C.POINTER(MrfPairArgs), C.c_void_p]
     lib.jatts_op_relpos_attention.argtypes = [C.POINTER(RelposAttentionArgs), C.c_void_p]
     lib.jatts_debug_set_trace.argtypes = [C.c_void_p]
+    lib.jatts_profile_end_classes.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
     lib.jatts_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int64)]
     if lib.jatts_abi_version() != 1:
@@ -171,3 +172,14 @@ def profile_end():
     a, b, c, d = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
     check(lib.jatts_profile_end(C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "profile_end")
     return dict(ms_bf16=a.value, n_bf16=b.value, ms_split=c.value, n_split=d.value)
+
+
+PROFILE_CLASSES = ("bf16_conv", "split_gemm", "attention", "layernorm", "dwconv_swish", "length_regulate", "output_conv")
+
+
+def profile_end_classes():
+    """-> {class: (ms, launches)} for every kernel class of include/jatts_b200.h::jatts_profile_end_classes"""
+    n = len(PROFILE_CLASSES)
+    ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+    check(lib.jatts_profile_end_classes(ms, cnt, n), "profile_end_classes")
+    return {name: (ms[i], cnt[i]) for i, name in enumerate(PROFILE_CLASSES)}

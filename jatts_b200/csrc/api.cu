@@ -85,8 +85,10 @@ extern "C" int jatts_profile_end(double* ms_bf16, int64_t* n_bf16, double* ms_sp
     JB_CUDA_OK(cudaEventSynchronize(e.e1));
     float t = 0.f;
     JB_CUDA_OK(cudaEventElapsedTime(&t, e.e0, e.e1));
-    ms[e.split] += t;
-    n[e.split] += 1;
+    if (e.split == 0 || e.split == 1) {
+      ms[e.split] += t;
+      n[e.split] += 1;
+    }
     cudaEventDestroy(e.e0);
     cudaEventDestroy(e.e1);
   }
@@ -95,6 +97,22 @@ extern "C" int jatts_profile_end(double* ms_bf16, int64_t* n_bf16, double* ms_sp
   if (n_bf16) *n_bf16 = n[0];
   if (ms_split) *ms_split = ms[1];
   if (n_split) *n_split = n[1];
+  return 0;
+}
+
+extern "C" int jatts_profile_end_classes(double* ms, int64_t* n, int32_t n_classes) {
+  JB_REQUIRE(ms && n && n_classes >= PROF_CLASSES, JATTS_E_INVALID, "profile_end_classes: need room for every class");
+  g_profile_on = false;
+  for (int i = 0; i < n_classes; ++i) { ms[i] = 0.0; n[i] = 0; }
+  for (auto& e : g_profile_events) {
+    JB_CUDA_OK(cudaEventSynchronize(e.e1));
+    float t = 0.f;
+    JB_CUDA_OK(cudaEventElapsedTime(&t, e.e0, e.e1));
+    if (e.split >= 0 && e.split < n_classes) { ms[e.split] += t; n[e.split] += 1; }
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+  g_profile_events.clear();
   return 0;
 }
 

@@ -594,6 +594,7 @@ int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const
   JB_PROPAGATE(make_tmap(&mpl, pos_lo, pos_rows, d_model, d_model, 128));
   JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(relpos_attention_tc_kernel), kSmemBytes));
   const int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  ProfileScope prof(s, PROF_ATTENTION);
   JB_CUDA_OK(launch_tc(relpos_attention_tc_kernel, grid, kAttThreads, kSmemBytes, s, 1, mxh, mxl, mvh, mvl, mph, mpl, P));
   JB_KERNEL_OK();
   return 0;

@@ -81,9 +81,28 @@ int conv_gemm_simt_debug(const ConvGemmProblem& p, cudaStream_t stream);
 
 int num_sms();
 
-// optional per-launch device timing of the tcgen05 kernel (jatts_profile_begin / jatts_profile_end)
-struct ProfileEvent { cudaEvent_t e0, e1; int split; };
+// optional per-launch device timing (jatts_profile_begin / jatts_profile_end*): CUDA events recorded around every
+// launch of a class of kernels on the launching stream; bench.py turns them into achieved TFLOP/s / GB/s
+enum : int { PROF_BF16_CONV = 0, PROF_SPLIT_GEMM = 1, PROF_ATTENTION = 2, PROF_LAYERNORM = 3, PROF_DWCONV = 4,
+             PROF_LENGTH_REGULATE = 5, PROF_OUTPUT_CONV = 6, PROF_CLASSES = 7 };
+struct ProfileEvent { cudaEvent_t e0, e1; int split; };   // split = PROF_* class
 extern bool g_profile_on;
 extern std::vector<ProfileEvent> g_profile_events;
+// RAII: e0 before the launch, e1 after it (no-op unless profiling is armed)
+struct ProfileScope {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t s;
+  int cls;
+  ProfileScope(cudaStream_t stream, int c) : s(stream), cls(c) {
+    if (!g_profile_on) return;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = e1 = nullptr; return; }
+    cudaEventRecord(e0, s);
+  }
+  ~ProfileScope() {
+    if (!e0) return;
+    cudaEventRecord(e1, s);
+    g_profile_events.push_back({e0, e1, cls});
+  }
+};
 
 }  // namespace jb

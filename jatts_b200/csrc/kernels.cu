@@ -1,5 +1,6 @@
 // Bandwidth-bound / small kernels of the synthesis path (CUDA cores, fp32 arithmetic).
 // Every kernel works on the packed-with-gaps row layout (common.cuh): gap rows are never written.
+#include "conv_gemm.cuh"
 #include "kernels.cuh"
 
 namespace jb {
@@ -147,6 +148,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int c, const float
 }
 int layernorm_rows(const float* x, int c, const float* gamma, const float* beta, float eps, RowLayout L, float* y,
                    bf16* hi, bf16* lo, int bf_ld, cudaStream_t s) {
+  ProfileScope prof(s, PROF_LAYERNORM);
   JB_REQUIRE(c % 4 == 0 && c <= 128 * LN_MAXV, -2, "layernorm: C must be a multiple of 4 and <= 512");
   JB_REQUIRE(bf_ld % 4 == 0, -2, "layernorm: bf_ld % 4");
   if (L.n_rows == 0) return 0;
@@ -157,6 +159,7 @@ int layernorm_rows(const float* x, int c, const float* gamma, const float* beta,
 }
 int ln_dot_rows(const float* x, int c, const float* gamma, const float* beta, float eps, const float* w, float b,
                 RowLayout L, float* out, cudaStream_t s) {
+  ProfileScope prof(s, PROF_LAYERNORM);
   JB_REQUIRE(c % 4 == 0 && c <= 128 * LN_MAXV, -2, "ln_dot: C must be a multiple of 4 and <= 512");
   if (L.n_rows == 0) return 0;
   layernorm_kernel<true><<<ceil_div(L.n_rows, 8), 256, 0, s>>>(x, c, gamma, beta, eps, L, nullptr, nullptr, nullptr, 4,
@@ -222,6 +225,7 @@ __global__ void dwconv_swish_kernel(const float* __restrict__ g, int c, const fl
 }
 int dwconv_swish(const float* g, int c, const float* wT, const float* bias, int k, RowLayout L, bf16* out_hi,
                  bf16* out_lo, int out_ld, cudaStream_t s) {
+  ProfileScope prof(s, PROF_DWCONV);
   JB_REQUIRE(c % 4 == 0 && out_ld % 4 == 0 && (k & 1) == 1, -2, "dwconv: C % 4, odd k");
   if (L.n_rows == 0) return 0;
   dwconv_swish_kernel<<<L.n_rows, 96, 0, s>>>(g, c, wT, bias, k, L, out_hi, out_lo, out_ld);
@@ -391,6 +395,7 @@ __global__ void length_regulate_kernel(const float* __restrict__ hs, const float
 int length_regulate(const float* hs, const float* pitch, const float* energy, const float* wp, const float* bp,
                     const float* we, const float* be, int d, float scale, RowLayout Ltext, const int* cum,
                     RowLayout Lframe, const int* frame_off, float* x_out, int* lr_index, cudaStream_t s) {
+  ProfileScope prof(s, PROF_LENGTH_REGULATE);
   JB_REQUIRE(d % 4 == 0, -2, "length_regulate: d % 4");
   if (Lframe.n_rows == 0) return 0;
   length_regulate_kernel<<<ceil_div(Lframe.n_rows, 8), 256, 0, s>>>(hs, pitch, energy, wp, bp, we, be, d, scale, Ltext,
@@ -560,6 +565,7 @@ output_conv32_tiled_kernel(const bf16* __restrict__ x, const float* __restrict__
 
 int output_conv_tanh(const bf16* x, int ld, int c, const float* w, float bias, int k, RowLayout L, int rate,
                      const int* frame_off, float* wave, short* pcm, cudaStream_t s) {
+  ProfileScope prof(s, PROF_OUTPUT_CONV);
   JB_REQUIRE(c % 8 == 0 && ld % 8 == 0 && k <= OC_MAXK, -2, "output_conv: C % 8, k <= 7");
   const long long total = static_cast<long long>(L.n_rows) * rate;
   if (total == 0) return 0;

@@ -77,3 +77,35 @@ def test_config4_vocoder_only_bulk_sharded():
     for i in (mine[0], mine[77]):
         ref = ohg.hifigan_forward(sd, cfg, mels[i])
         assert ohg.ac_snr_db(ref, out[i].cpu()) >= SNR_DB
+
+
+@pytest.mark.gpu
+def test_config4_sharded_output_is_bit_identical_across_world_sizes():
+    """SURVEY section 4 / VERDICT r1 missing #3: the N-way sharded run returns the bytes of the 1-GPU run.  Ranks are
+    independent processes running this same code on their shard (no collective on the data path), so the partitions of
+    world sizes 1, 2, 4 and 8 are replayed here rank by rank with bench.py's batching (length-sorted, 128 clips per
+    launch) and compared clip by clip."""
+    cfg = recipes.HIFIGAN_V1_HOP300
+    gen = jatts_b200.HiFiGANGenerator(**cfg)
+    gen.load_state_dict(recipes.make_hifigan_state_dict(cfg, 0))
+    gen = gen.eval().to("cuda")
+    g = torch.Generator().manual_seed(4)
+    lens = torch.randint(200, 401, (10000,), generator=g).tolist()[:384]        # the first 384 clips of the config-4 list
+    mels = [recipes.make_mel(t, i).cuda() for i, t in enumerate(lens)]
+
+    def run_world(world):
+        out = {}
+        for shard in jatts_b200.shard_utterances(lens, world):
+            order = sorted(shard, key=lambda i: (lens[i], i))
+            for s in range(0, len(order), 128):
+                b = order[s:s + 128]
+                for i, y in zip(b, gen.inference_batch([mels[i] for i in b])):
+                    out[i] = y
+        return out
+
+    base = run_world(1)
+    assert sorted(base) == list(range(len(lens)))
+    for world in (2, 4, 8):
+        got = run_world(world)
+        for i in range(len(lens)):
+            assert torch.equal(got[i], base[i]), f"world {world}: clip {i} differs from the 1-GPU bytes"
