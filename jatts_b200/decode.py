@@ -10,8 +10,13 @@ With the B200 path at ~10^4 x real time that host loop is the whole run time, so
     ``max_tokens`` tokens -- padding never exists on the device, the bound only keeps a batch's memory flat),
   * runs ``FastSpeech2.inference_batch`` -> ``Vocoder.decode_batch(pcm16=True)``: the float -> PCM_16 conversion
     libsndfile would do on the host (``lrintf(y * 0x7FFF)``) is fused into the generator's output convolution,
-  * copies the int16 samples to pinned host memory asynchronously and writes the ``.wav`` files from a writer
-    thread while the next batch is on the GPU.
+  * copies the int16 samples to a ring of pinned host buffers asynchronously and writes the ``.wav`` files from a
+    writer thread while the next batch is on the GPU,
+  * shards the utterances over the GPUs of the box (one process per GPU, ``torchrun`` or ``--rank/--world-size``;
+    deterministic greedy partition by length, no communication: jatts_b200/shard.py) -- the reference pins stage 4 to
+    ``n_gpus=1`` (egs/jsut/tts1/run.sh:246),
+  * looks speaker embeddings up per ``ref_wav_path`` through a cache, so a multi-speaker run extracts (or loads) each
+    reference once instead of once per utterance (tts_decode.py:209-212 calls the extractor inside the loop).
 
 Row *i* of a batch equals the reference's per-utterance result, so the wav files hold the
 samples stage 4 would have written.  Plots (``outs/*.png``) are not produced: matplotlib is not part of this path.
@@ -107,7 +112,7 @@ def write_wav_pcm16(path: str, samples, sampling_rate: int) -> None:
 
 def read_stats(path, prefix: str) -> Tuple["object", "object"]:
     """``{prefix}_mean`` / ``{prefix}_scale`` of the text2mel stats file (tts_decode.py:160-164): the recipe's
-    ``stats.h5`` (needs h5py, as the reference does) or an ``.npz`` with the same keys."""
+    ``stats.h5`` (h5py when installed, else the built-in reader jatts_b200/_h5lite.py) or an ``.npz`` with the same keys."""
     if isinstance(path, dict):
         return path[f"{prefix}_mean"], path[f"{prefix}_scale"]
     if str(path).endswith(".npz"):
@@ -117,10 +122,73 @@ def read_stats(path, prefix: str) -> Tuple["object", "object"]:
         return z[f"{prefix}_mean"], z[f"{prefix}_scale"]
     try:
         import h5py
-    except ImportError as e:
-        raise RuntimeError("reading stats.h5 needs h5py; convert it to an .npz with the same keys") from e
+    except ImportError:
+        from ._h5lite import read_hdf5
+
+        return read_hdf5(path, f"{prefix}_mean"), read_hdf5(path, f"{prefix}_scale")
     with h5py.File(path, "r") as f:
         return f[f"{prefix}_mean"][()], f[f"{prefix}_scale"][()]
+
+
+class SpeakerEmbeddingCache:
+    """Speaker embeddings for the decode loop (tts_decode.py:146-152, 209-212).  The reference runs its extractor
+    (``SpeechBrainSpkEmbExtractor.forward(ref_wav_path)``, spkemb_speechbrain.py:14-28, an ECAPA-TDNN on the CPU) once
+    PER UTTERANCE inside the loop; the embedding only depends on the reference wav, so it is looked up here by key:
+
+      * ``table``: precomputed embeddings keyed by ``sample_id`` or ``ref_wav_path`` (an ``.npz``), and / or
+      * ``extractor``: any callable ``path -> 1-D embedding`` (e.g. the reference's extractor object's ``forward``) that
+        is called once per distinct ``ref_wav_path`` and memoised.
+
+    The extractor itself is a third-party model (speechbrain, downloaded at run time) and is out of scope."""
+
+    def __init__(self, table=None, extractor=None):
+        self.table = dict(table) if table is not None else {}
+        self.extractor = extractor
+        self.calls = 0
+
+    def __call__(self, item: dict):
+        import torch
+
+        for key in (item.get("sample_id"), item.get("ref_wav_path")):
+            if key is not None and key in self.table:
+                return torch.as_tensor(self.table[key], dtype=torch.float32).reshape(-1)
+        ref = item.get("ref_wav_path")
+        if self.extractor is None or ref is None:
+            raise KeyError(f"no speaker embedding for {item.get('sample_id')!r} (neither a table entry nor an extractor / ref_wav_path)")
+        self.calls += 1
+        emb = torch.as_tensor(self.extractor(ref), dtype=torch.float32).reshape(-1)
+        self.table[ref] = emb
+        return emb
+
+
+class PinnedRing:
+    """A few reusable pinned host buffers: a fresh ``pin_memory()`` per batch is a page-locking system call (and a
+    synchronisation) each time.  A buffer is reused when the consumer has released it (``event`` / writer done)."""
+
+    def __init__(self, dtype, slots: int = 4):
+        import torch
+
+        self.dtype, self.slots = dtype, slots
+        self.bufs = [torch.empty(0, dtype=dtype).pin_memory() for _ in range(slots)]
+        self.free = [threading.Event() for _ in range(slots)]
+        for e in self.free:
+            e.set()
+        self.i = 0
+
+    def take(self, n: int):
+        """-> (slot index, pinned 1-D view of n elements); blocks until the slot's previous user released it"""
+        import torch
+
+        k = self.i
+        self.i = (self.i + 1) % self.slots
+        self.free[k].wait()
+        self.free[k].clear()
+        if self.bufs[k].numel() < n:
+            self.bufs[k] = torch.empty(max(n, 2 * self.bufs[k].numel()), dtype=self.dtype).pin_memory()
+        return k, self.bufs[k][:n]
+
+    def release(self, k: int):
+        self.free[k].set()
 
 
 class WavWriter:
@@ -140,20 +208,24 @@ class WavWriter:
             if job is None:
                 return
             try:
-                host, event, entries, sr = job
-                if event is not None:
-                    event.synchronize()
-                arr = host.numpy()
-                for path, a, b in entries:
-                    write_wav_pcm16(path, arr[a:b], sr)
-                    self.files += 1
+                host, event, entries, sr, done = job
+                try:
+                    if event is not None:
+                        event.synchronize()
+                    arr = host.numpy()
+                    for path, a, b in entries:
+                        write_wav_pcm16(path, arr[a:b], sr)
+                        self.files += 1
+                finally:
+                    if done is not None:
+                        done()      # the pinned buffer goes back to the ring
             except BaseException as e:  # surfaced by close()
                 self.error = e
 
-    def submit(self, host, event, entries, sr):
+    def submit(self, host, event, entries, sr, done=None):
         if self.error is not None:
             raise self.error
-        self.q.put((host, event, entries, sr))
+        self.q.put((host, event, entries, sr, done))
 
     def close(self):
         self.q.put(None)
@@ -166,54 +238,97 @@ class WavWriter:
 # the decode loop
 # --------------------------------------------------------------------------------------------------------------
 def decode_items(model, vocoder, items: Sequence[dict], outdir: str, sampling_rate: int, device, max_utts: int = 64,
-                 max_tokens: int = 8192, spembs: Optional[Dict[str, "object"]] = None) -> dict:
-    """Synthesise ``items`` (dicts with ``sample_id`` and ``token_indices``) into ``outdir/wav/<sample_id>.wav``.
-    ``spembs`` maps ``sample_id`` (or the item's ``ref_wav_path``) to a speaker embedding for multi-speaker models.
-    Returns counters (utterances, batches, frames, audio seconds, wall seconds)."""
+                 max_tokens: int = 8192, spembs=None, rank: int = 0, world_size: int = 1) -> dict:
+    """Synthesise this rank's share of ``items`` (dicts with ``sample_id`` and ``token_indices``) into
+    ``outdir/wav/<sample_id>.wav``.  ``spembs``: a ``SpeakerEmbeddingCache`` (or a plain dict keyed by ``sample_id`` /
+    ``ref_wav_path``) for multi-speaker models.  With ``world_size > 1`` every rank calls this with the same ``items``
+    and decodes the utterances ``shard_utterances`` assigns to it (no communication; each file is written by exactly
+    one rank).  Returns counters (utterances, batches, frames, audio seconds, wall seconds) of this rank."""
     import torch
+
+    from .shard import shard_utterances
 
     wav_dir = os.path.join(outdir, "wav")
     os.makedirs(wav_dir, exist_ok=True)
-    lengths = [len(it["token_indices"]) for it in items]
-    batches = plan_batches(lengths, max_utts, max_tokens)
+    all_lengths = [len(it["token_indices"]) for it in items]
+    mine = shard_utterances(all_lengths, world_size)[rank] if world_size > 1 else list(range(len(items)))
+    lengths = [all_lengths[j] for j in mine]
+    batches = [[mine[k] for k in b] for b in plan_batches(lengths, max_utts, max_tokens)]
+    if spembs is not None and not callable(spembs):
+        spembs = SpeakerEmbeddingCache(table=spembs)
     writer = WavWriter()
     hop = vocoder.model.hop
     frames_total, t0 = 0, time.time()
     copy_stream = torch.cuda.Stream(device=device)
+    tok_ring, pcm_ring = PinnedRing(torch.long, 2), PinnedRing(torch.int16, 4)
+    skipped: List[str] = []
+
+    def run_batch(batch):
+        nonlocal frames_total
+        n_tok = sum(all_lengths[j] for j in batch)
+        tk, tok_host = tok_ring.take(n_tok)
+        tok_host.copy_(torch.tensor([t for j in batch for t in items[j]["token_indices"]], dtype=torch.long))
+        tok = tok_host.to(device, non_blocking=True)
+        h2d = torch.cuda.Event()
+        h2d.record()
+        texts = list(tok.split([all_lengths[j] for j in batch]))
+        sp = None
+        if model.spk_embed_dim is not None:
+            if spembs is None:
+                raise ValueError("the model is speaker conditioned: pass speaker embeddings (--spkemb-npz)")
+            sp = torch.stack([spembs(items[j]) for j in batch]).to(device)
+        try:
+            outs = model.inference_batch(texts, spembs=sp)
+        finally:
+            h2d.synchronize()
+            tok_ring.release(tk)
+        pcm = vocoder.decode_batch([o["feat_gen"] for o in outs], pcm16=True)
+        flat = torch.cat(pcm)
+        pk, host = pcm_ring.take(flat.numel())
+        done = torch.cuda.Event()
+        copy_stream.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(copy_stream):
+            host.copy_(flat, non_blocking=True)
+            flat.record_stream(copy_stream)
+            done.record(copy_stream)
+        entries, o = [], 0
+        for j, y in zip(batch, pcm):
+            n = int(y.numel())
+            entries.append((os.path.join(wav_dir, f"{items[j]['sample_id']}.wav"), o, o + n))
+            o += n
+            frames_total += n // hop
+        writer.submit(host, done, entries, sampling_rate, done=lambda k=pk: pcm_ring.release(k))
+
     try:
         for batch in batches:
-            tok_host = torch.tensor([t for j in batch for t in items[j]["token_indices"]], dtype=torch.long).pin_memory()
-            tok = tok_host.to(device, non_blocking=True)
-            texts = list(tok.split([lengths[j] for j in batch]))
-            sp = None
-            if model.spk_embed_dim is not None:
-                if spembs is None:
-                    raise ValueError("the model is speaker conditioned: pass speaker embeddings (--spkemb-npz)")
-                keys = [items[j]["sample_id"] if items[j]["sample_id"] in spembs else items[j].get("ref_wav_path") for j in batch]
-                sp = torch.stack([torch.as_tensor(spembs[k], dtype=torch.float32).reshape(-1) for k in keys]).to(device)
-            outs = model.inference_batch(texts, spembs=sp)
-            pcm = vocoder.decode_batch([o["feat_gen"] for o in outs], pcm16=True)
-            flat = torch.cat(pcm)
-            host = torch.empty(flat.numel(), dtype=torch.int16).pin_memory()
-            done = torch.cuda.Event()
-            copy_stream.wait_stream(torch.cuda.current_stream(device))
-            with torch.cuda.stream(copy_stream):
-                host.copy_(flat, non_blocking=True)
-                flat.record_stream(copy_stream)
-                done.record(copy_stream)
-            entries, o = [], 0
-            for j, y in zip(batch, pcm):
-                n = int(y.numel())
-                entries.append((os.path.join(wav_dir, f"{items[j]['sample_id']}.wav"), o, o + n))
-                o += n
-                frames_total += n // hop
-            writer.submit(host, done, entries, sampling_rate)
+            try:
+                run_batch(batch)
+            except NotImplementedError as e:
+                # an utterance of the batch expands to more frames than the model's max_len: the reference has no such
+                # limit (it extends its positional table), so do not lose the rest of the batch -- retry one by one
+                # and report the utterances that really do not fit (raise --max-len to decode them)
+                if "max_len" not in str(e) or len(batch) == 1:
+                    if "max_len" in str(e):
+                        skipped.append(items[batch[0]]["sample_id"])
+                        logging.warning("utterance %s needs more than max_len frames: skipped (%s)", skipped[-1], e)
+                        continue
+                    raise
+                for j in batch:
+                    try:
+                        run_batch([j])
+                    except NotImplementedError as e1:
+                        if "max_len" not in str(e1):
+                            raise
+                        skipped.append(items[j]["sample_id"])
+                        logging.warning("utterance %s needs more than max_len frames: skipped (%s)", skipped[-1], e1)
     finally:
         writer.close()
     wall = time.time() - t0
     audio_s = frames_total * hop / float(sampling_rate)
-    return {"utterances": len(items), "batches": len(batches), "frames": frames_total, "audio_seconds": audio_s,
-            "wall_seconds": wall, "files": writer.files}
+    return {"utterances": len(mine) - len(skipped), "batches": len(batches), "frames": frames_total, "audio_seconds": audio_s,
+            "wall_seconds": wall, "files": writer.files, "skipped": skipped, "rank": rank, "world_size": world_size,
+            "utterances_per_second": (len(mine) - len(skipped)) / max(wall, 1e-9),
+            "audio_seconds_per_second": audio_s / max(wall, 1e-9)}
 
 
 def main(argv=None) -> int:
@@ -236,6 +351,12 @@ def main(argv=None) -> int:
     ap.add_argument("--max-tokens", type=int, default=8192, help="summed tokens per batch")
     ap.add_argument("--spkemb-npz", default=None, type=str,
                     help="precomputed speaker embeddings keyed by sample_id or ref_wav_path (multi-speaker models)")
+    ap.add_argument("--max-len", type=int, default=2048,
+                    help="longest utterance in mel frames the engine is built for (<= 5000, the reference's positional table)")
+    ap.add_argument("--rank", type=int, default=int(os.environ.get("RANK", "0")),
+                    help="this process's shard (default: torchrun's RANK)")
+    ap.add_argument("--world-size", type=int, default=int(os.environ.get("WORLD_SIZE", "1")),
+                    help="number of processes sharing the csv, one per GPU (default: torchrun's WORLD_SIZE)")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.DEBUG if args.verbose > 1 else logging.INFO if args.verbose > 0 else logging.WARN,
                         format="%(asctime)s (%(module)s:%(lineno)d) %(levelname)s: %(message)s")
@@ -249,10 +370,14 @@ def main(argv=None) -> int:
         raise NotImplementedError(f"model_type {config['model_type']}: only FastSpeech2 has a B200 path")
     if not torch.cuda.is_available():
         raise RuntimeError("jatts_b200.decode needs a CUDA device (there is no CPU fallback)")
-    device = torch.device("cuda")
+    if not 0 <= args.rank < args.world_size:
+        raise ValueError("--rank must be in [0, --world-size)")
+    local = int(os.environ.get("LOCAL_RANK", args.rank % max(torch.cuda.device_count(), 1)))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
     items = read_items(args.csv, args.token_column, TokenIDConverter(args.token_list))
     logging.info(f"Dataset size = {len(items)}.")
-    model = jatts_b200.FastSpeech2(**config["model_params"])
+    model = jatts_b200.FastSpeech2(**config["model_params"], max_len=args.max_len)
     model.load_state_dict(torch.load(args.checkpoint, map_location="cpu")["model"])
     model = model.eval().to(device)
     logging.info(f"Loaded model parameters from {args.checkpoint}.")
@@ -266,12 +391,17 @@ def main(argv=None) -> int:
     if args.spkemb_npz:
         import numpy as np
 
-        spembs = dict(np.load(args.spkemb_npz))
+        spembs = SpeakerEmbeddingCache(table=dict(np.load(args.spkemb_npz)))
     res = decode_items(model, vocoder, items, args.outdir, vocoder.config["sampling_rate"], device, args.max_utts,
-                       args.max_tokens, spembs)
-    logging.info("decoded %d utterances in %d batches: %.1f s of audio in %.2f s (%.0f x real time)" % (
-        res["utterances"], res["batches"], res["audio_seconds"], res["wall_seconds"],
-        res["audio_seconds"] / max(res["wall_seconds"], 1e-9)))
+                       args.max_tokens, spembs, rank=args.rank, world_size=args.world_size)
+    logging.info("rank %d/%d decoded %d utterances in %d batches: %.1f s of audio in %.2f s (%.0f x real time, %.0f utterances/s)%s" % (
+        args.rank, args.world_size, res["utterances"], res["batches"], res["audio_seconds"], res["wall_seconds"],
+        res["audio_seconds_per_second"], res["utterances_per_second"],
+        f"; skipped (longer than --max-len): {res['skipped']}" if res["skipped"] else ""))
+    with open(os.path.join(args.outdir, f"decode_stats.rank{args.rank}.json"), "w") as f:
+        import json
+
+        json.dump(res, f)
     return 0
 
 

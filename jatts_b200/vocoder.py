@@ -231,7 +231,9 @@ class HiFiGANGenerator(torch.nn.Module):
 
 
 def _read_stats(stats):
-    """``stats`` may be a dict (tests), an .npz path, or the recipe's stats.h5 (needs h5py)."""
+    """``stats`` may be a dict (tests), an .npz path, or the recipe's ``stats.h5`` (vocoder.py:47-54 reads ``mean`` and
+    ``scale`` with ``read_hdf5``): h5py when it is installed, else the built-in reader of the 'earliest' HDF5 format
+    (jatts_b200/_h5lite.py)."""
     if isinstance(stats, dict):
         return stats["mean"], stats["scale"]
     if str(stats).endswith(".npz"):
@@ -241,8 +243,10 @@ def _read_stats(stats):
         return z["mean"], z["scale"]
     try:
         import h5py
-    except ImportError as e:  # same failure mode as jatts.utils.read_hdf5 without its dependency
-        raise RuntimeError("reading stats.h5 needs h5py; pass a dict or an .npz instead") from e
+    except ImportError:
+        from ._h5lite import read_hdf5
+
+        return read_hdf5(stats, "mean"), read_hdf5(stats, "scale")
     with h5py.File(stats, "r") as f:
         return f["mean"][()], f["scale"][()]
 

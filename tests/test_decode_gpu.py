@@ -9,6 +9,7 @@ import torch
 import yaml
 
 import jatts_b200
+from h5_writer import write_h5
 from jatts_b200 import decode
 from oracle import fs2 as ofs2
 from oracle import hifigan as ohg
@@ -55,8 +56,9 @@ def test_cli_writes_the_per_utterance_samples(tmp_path):
         texts.append(torch.tensor(ids, dtype=torch.long))
         rows.append(f"utt{i}," + " ".join(toks))
     (tmp_path / "dev.csv").write_text("\n".join(rows) + "\n", encoding="utf-8")
-    np.savez(tmp_path / "stats.npz", mel_mean=tstats["mean"].numpy(), mel_scale=tstats["scale"].numpy())
-    np.savez(tmp_path / "voc_stats.npz", mean=vstats["mean"].numpy(), scale=vstats["scale"].numpy())
+    # the recipe's statistics files are HDF5 (compute_statistics.py / parallel_wavegan): read without h5py
+    write_h5(tmp_path / "stats.h5", {"mel_mean": tstats["mean"].numpy(), "mel_scale": tstats["scale"].numpy()})
+    write_h5(tmp_path / "voc_stats.h5", {"mean": vstats["mean"].numpy(), "scale": vstats["scale"].numpy()})
     torch.save({"model": {"generator": hsd}}, tmp_path / "voc.pkl")
     with open(tmp_path / "voc_config.yml", "w") as f:
         yaml.safe_dump({"generator_type": "HiFiGANGenerator", "sampling_rate": 24000,
@@ -67,9 +69,9 @@ def test_cli_writes_the_per_utterance_samples(tmp_path):
         yaml.safe_dump({"model_type": "FastSpeech2", "model_params": dict(cfg), "out_feat_type": "mel", "feat_list": ["mel"],
                         "sampling_rate": 24000,
                         "vocoder": {"checkpoint": str(tmp_path / "voc.pkl"), "config": str(tmp_path / "voc_config.yml"),
-                                    "stats": str(tmp_path / "voc_stats.npz")}}, f)
+                                    "stats": str(tmp_path / "voc_stats.h5")}}, f)
     out = tmp_path / "out"
-    rc = decode.main(["--csv", str(tmp_path / "dev.csv"), "--stats", str(tmp_path / "stats.npz"),
+    rc = decode.main(["--csv", str(tmp_path / "dev.csv"), "--stats", str(tmp_path / "stats.h5"),
                       "--token-list", str(tmp_path / "tokens.txt"), "--token-column", "phonemes", "--outdir", str(out),
                       "--checkpoint", str(tmp_path / "checkpoint-1steps.pkl"), "--max-utts", "3", "--verbose", "0"])
     assert rc == 0
@@ -97,3 +99,34 @@ def test_cli_writes_the_per_utterance_samples(tmp_path):
         assert got.shape[0] == yref.shape[0] == int(ref["duration"].sum()) * 6
         snr = ohg.ac_snr_db(yref, torch.from_numpy(got))
         assert snr > 35.0, f"utt{i}: AC-SNR {snr:.1f} dB vs the oracle"
+
+    # ---- two processes' worth of sharding (one per GPU in production: torchrun sets RANK / WORLD_SIZE): every file is
+    #      written by exactly one rank and holds the bytes of the single-process run
+    out2 = tmp_path / "out2"
+    for r in range(2):
+        assert decode.main(["--csv", str(tmp_path / "dev.csv"), "--stats", str(tmp_path / "stats.h5"), "--token-list",
+                            str(tmp_path / "tokens.txt"), "--token-column", "phonemes", "--outdir", str(out2), "--checkpoint",
+                            str(tmp_path / "checkpoint-1steps.pkl"), "--verbose", "0", "--rank", str(r), "--world-size", "2"]) == 0
+    import json
+    counts = [json.load(open(out2 / f"decode_stats.rank{r}.json"))["utterances"] for r in range(2)]
+    assert sum(counts) == len(lens) and min(counts) >= 1
+    for i in range(len(lens)):
+        assert (out2 / "wav" / f"utt{i}.wav").read_bytes() == (out / "wav" / f"utt{i}.wav").read_bytes()
+
+
+@pytest.mark.gpu
+def test_utterance_longer_than_max_len_is_reported_not_fatal(tmp_path):
+    """one over-long utterance used to abort the whole run part-way; now the rest of its batch is decoded
+    and the offender is reported (the reference itself has no length limit: --max-len raises ours to 5000 frames)."""
+    cfg, hcfg = recipes.JSUT_FS2, recipes.HIFIGAN_TINY
+    model = jatts_b200.FastSpeech2(**cfg, max_len=128)
+    model.load_state_dict(recipes.make_fs2_state_dict(cfg, seed=0, duration_recipe="A"))
+    model = model.eval().to("cuda")
+    st = recipes.make_stats(1)
+    voc = jatts_b200.Vocoder(recipes.make_hifigan_state_dict(hcfg, 0), {"generator_type": "HiFiGANGenerator",
+                             "generator_params": dict(hcfg), "sampling_rate": 24000}, st, "cuda", trg_stats=st)
+    items = [{"sample_id": f"u{i}", "token_indices": recipes.make_phonemes(n, 50 + i, cfg["idim"]).tolist()}
+             for i, n in enumerate([10, 12, 40, 11])]          # 40 tokens -> ~240 frames > 128
+    res = decode.decode_items(model, voc, items, str(tmp_path), 24000, torch.device("cuda"), max_utts=8)
+    assert res["skipped"] == ["u2"] and res["files"] == 3
+    assert sorted(p.name for p in (tmp_path / "wav").iterdir()) == ["u0.wav", "u1.wav", "u3.wav"]

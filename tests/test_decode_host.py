@@ -67,3 +67,34 @@ def test_read_stats_npz_and_dict(tmp_path):
     assert np.array_equal(a, m) and np.array_equal(b, s)
     a, b = decode.read_stats({"mel_mean": m, "mel_scale": s}, "mel")
     assert a is m and b is s
+
+
+def test_speaker_embedding_cache_calls_the_extractor_once_per_reference():
+    """tts_decode.py:209-212 runs the extractor per utterance; the cache runs it per distinct ref_wav_path"""
+    import torch
+    calls = []
+
+    def extractor(path):
+        calls.append(path)
+        return torch.full((192,), float(len(path)))
+
+    cache = decode.SpeakerEmbeddingCache(table={"uttX": torch.zeros(192)}, extractor=extractor)
+    items = [{"sample_id": f"u{i}", "ref_wav_path": f"/spk{i % 2}.wav"} for i in range(6)] + [{"sample_id": "uttX", "ref_wav_path": "/z.wav"}]
+    embs = [cache(it) for it in items]
+    assert calls == ["/spk0.wav", "/spk1.wav"] and cache.calls == 2
+    assert float(embs[-1].abs().sum()) == 0.0 and embs[0].shape == (192,)
+    with pytest.raises(KeyError):
+        decode.SpeakerEmbeddingCache()({"sample_id": "a"})
+
+
+def test_pinned_ring_reuses_released_buffers():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("pinned memory needs a CUDA runtime")
+    ring = decode.PinnedRing(torch.int16, slots=2)
+    k0, a = ring.take(100)
+    k1, b = ring.take(50)
+    assert a.is_pinned() and a.numel() == 100 and k0 != k1
+    ring.release(k0)
+    k2, c = ring.take(80)
+    assert k2 == k0 and c.data_ptr() == a.data_ptr()
