@@ -290,7 +290,7 @@ static int conformer_stack(jatts_fs2* h, const ConformerW& W, const RowLayout& L
     ConvGemmEpilogue eg{};
     eg.act = ACT_GLU; eg.out_f32 = h->g; eg.out_f32_ld = d;
     JB_PROPAGATE(run_conv(Lw.pw1, h->h_hi, h->h_lo, d, L, eg, s));
-    JB_PROPAGATE(dwconv_swish(h->g, d, Lw.dw_wT, Lw.dw_b, Lw.dw_k, L, h->c_hi, h->c_lo, d, s));
+    JB_PROPAGATE(dwconv_swish(h->g, d, Lw.dw_wT, Lw.dw_b, Lw.dw_k, L, max_len, h->c_hi, h->c_lo, d, s));
     ConvGemmEpilogue e2{};
     e2.res_f32 = h->x; e2.res_ld = d; e2.out_f32 = h->x; e2.out_f32_ld = d;
     JB_PROPAGATE(run_conv(Lw.pw2, h->c_hi, h->c_lo, d, L, e2, s));

@@ -1,5 +1,7 @@
 // Bandwidth-bound / small kernels of the synthesis path (CUDA cores, fp32 arithmetic).
 // Every kernel works on the packed-with-gaps row layout (common.cuh): gap rows are never written.
+#include <cstdlib>
+
 #include "conv_gemm.cuh"
 #include "kernels.cuh"
 
@@ -189,6 +191,74 @@ int split_rows(const float* x, int c, RowLayout L, bf16* hi, bf16* lo, int bf_ld
 // ------------------------------------------------------------------------------------------------
 // depthwise conv + folded BatchNorm + Swish
 // ------------------------------------------------------------------------------------------------
+// One CTA = one strip of K*M consecutive frames of one utterance, all channels.  The strip plus its K-1 halo rows is
+// staged in shared memory with coalesced 16-byte loads (zeros outside the utterance = the convolution's own padding);
+// then thread c walks down the strip for channel c with the K-row window and the K taps in registers (the fully
+// unrolled (p, j) loops make every window index static): one conflict-free shared-memory load per output instead of
+// K global loads through L1 (31 at the decoder's kernel size), and every input row leaves L2 once per strip.
+template <int K, int M>
+__global__ void __launch_bounds__(256)
+dwconv_swish_strip_kernel(const float* __restrict__ g, int c, const float* __restrict__ wT, const float* __restrict__ bias,
+                          RowLayout L, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int out_ld) {
+  constexpr int PAD = (K - 1) / 2, TR = K * M, ROWS = TR + K - 1;
+  extern __shared__ __align__(16) float dw_tile[];   // [ROWS][cb]: this CTA's block of channels
+  const int b = blockIdx.y;
+  const int cb = blockDim.x;                          // channels per CTA (multiple of 32, divides c)
+  const int c0 = blockIdx.z * cb;
+  const int T = L.seg_len[b];
+  const int r0 = blockIdx.x * TR;                     // first output frame of the strip (utterance-relative)
+  if (r0 >= T) return;
+  const long long base = L.seg_start[b];
+  const int c4n = cb >> 2;
+  const int n4 = ROWS * c4n;
+  for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {   // 4 independent 16-byte loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int rr = i / c4n, q = i - rr * c4n;
+      const int t = r0 - PAD + rr;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4 && t >= 0 && t < T) v[u] = reinterpret_cast<const float4*>(g + (base + t) * c + c0)[q];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n4) reinterpret_cast<float4*>(dw_tile)[i] = v[u];
+    }
+  }
+  __syncthreads();
+  const int ch = c0 + threadIdx.x;
+  float w[K], win[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) w[j] = wT[j * c + ch];
+  const float bv = bias[ch];
+  const float* col = dw_tile + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < K - 1; ++j) win[j] = col[j * cb];
+#pragma unroll 1
+  for (int m = 0; m < M; ++m) {
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+      const int o = m * K + p;                        // output row of the strip; its newest input is tile row o + K - 1
+      win[(K - 1 + p) % K] = col[(o + K - 1) * cb];
+      float acc = bv;
+#pragma unroll
+      for (int j = 0; j < K; ++j) acc = fmaf(win[(p + j) % K], w[j], acc);
+      const float y = acc * (1.0f / (1.0f + __expf(-acc)));   // swish.py:13-18 (2 ulp exp: far inside the 1e-3 budget)
+      const float yn = __shfl_down_sync(0xffffffffu, y, 1);  // even lanes store a channel pair (c is even)
+      const int t = r0 + o;
+      if (t < T && (ch & 1) == 0) {
+        uint32_t hw, lw;
+        split_pair16_sat(y, yn, hw, lw);
+        *reinterpret_cast<uint32_t*>(out_hi + (base + t) * out_ld + ch) = hw;
+        if (out_lo) *reinterpret_cast<uint32_t*>(out_lo + (base + t) * out_ld + ch) = lw;
+      }
+    }
+  }
+}
+
+// generic tap count (no shipped configuration): one CTA per row, taps re-read through L1
 __global__ void dwconv_swish_kernel(const float* __restrict__ g, int c, const float* __restrict__ wT,
                                     const float* __restrict__ bias, int k, RowLayout L, bf16* __restrict__ out_hi,
                                     bf16* __restrict__ out_lo, int out_ld) {
@@ -223,11 +293,35 @@ __global__ void dwconv_swish_kernel(const float* __restrict__ g, int c, const fl
     }
   }
 }
-int dwconv_swish(const float* g, int c, const float* wT, const float* bias, int k, RowLayout L, bf16* out_hi,
+int dwconv_swish(const float* g, int c, const float* wT, const float* bias, int k, RowLayout L, int max_len, bf16* out_hi,
                  bf16* out_lo, int out_ld, cudaStream_t s) {
   ProfileScope prof(s, PROF_DWCONV);
   JB_REQUIRE(c % 4 == 0 && out_ld % 4 == 0 && (k & 1) == 1, -2, "dwconv: C % 4, odd k");
-  if (L.n_rows == 0) return 0;
+  if (L.n_rows == 0 || L.nseg == 0) return 0;
+  static const bool generic_only = getenv("JATTS_B200_DWCONV_GENERIC") != nullptr;   // A/B switch for profiling
+  if (!generic_only && c % 32 == 0 && max_len > 0 && (k == 31 || k == 7)) {
+    // channels per CTA: the largest multiple of 32 <= 192 that divides c (3 CTAs of 70 KB per SM at c = 384, k = 31:
+    // one CTA's tile load runs under the others' arithmetic)
+    int cb = 0;
+    for (int t = 192; t >= 32; t -= 32)
+      if (c % t == 0) { cb = t; break; }
+    JB_REQUIRE(cb > 0, -2, "dwconv: C must be a multiple of 32");
+    if (k == 31) {
+      constexpr int M = 2;
+      const int smem = (31 * M + 30) * cb * 4;
+      JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(dwconv_swish_strip_kernel<31, M>), smem));
+      dim3 grid(ceil_div(max_len, 31 * M), L.nseg, c / cb);
+      dwconv_swish_strip_kernel<31, M><<<grid, cb, smem, s>>>(g, c, wT, bias, L, out_hi, out_lo, out_ld);
+    } else {
+      constexpr int M = 9;
+      const int smem = (7 * M + 6) * cb * 4;
+      JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(dwconv_swish_strip_kernel<7, M>), smem));
+      dim3 grid(ceil_div(max_len, 7 * M), L.nseg, c / cb);
+      dwconv_swish_strip_kernel<7, M><<<grid, cb, smem, s>>>(g, c, wT, bias, L, out_hi, out_lo, out_ld);
+    }
+    JB_KERNEL_OK();
+    return 0;
+  }
   dwconv_swish_kernel<<<L.n_rows, 96, 0, s>>>(g, c, wT, bias, k, L, out_hi, out_lo, out_ld);
   JB_KERNEL_OK();
   return 0;

@@ -38,7 +38,8 @@ int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const
 
 // depthwise Conv1d (BatchNorm folded into wT/bias on the host) -> Swish (convolution.py:74-75)
 // g: [rows, C] fp32 (GLU output), wT: [k][C], out: hi/lo bf16
-int dwconv_swish(const float* g, int c, const float* wT, const float* bias, int k, RowLayout L, bf16* out_hi,
+// max_len >= every utterance length (sizes the strip grid)
+int dwconv_swish(const float* g, int c, const float* wT, const float* bias, int k, RowLayout L, int max_len, bf16* out_hi,
                  bf16* out_lo, int out_ld, cudaStream_t s);
 
 // hs[row,:] += proj(normalize(spemb[b])) (fastspeech2.py:737-761, "add")
