@@ -133,8 +133,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint64_t* w2_full = t_empty + 2;          // [8]
   uint64_t* w2_empty = w2_full + kMaxRB;    // [8]
   uint64_t* w_full = w2_empty + kMaxRB;     // [1]
-  uint64_t* e1_turn = w_full + 1;           // [1] one t slab + two issuers: orders the E1 groups' t_empty waits
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e1_turn + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -166,7 +165,6 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_init(&w2_empty[i], 1);
     }
     mbar_init(w_full, 1);
-    mbar_init(e1_turn, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -176,7 +174,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // the t slabs' 16 tail rows are read by the shifted conv2 taps but never written: zero everything once
-  for (int i = threadIdx.x; i < P.nt * K::T_BYTES / 16; i += blockDim.x)
+  for (int i = threadIdx.x; i < P.nt * K::T_BYTES / 16; i += kThreadsP)
     sts128(smem_u32(t_base) + static_cast<uint32_t>(i) * 16u, make_uint4(0u, 0u, 0u, 0u));
   fence_proxy_async_smem();
   tc_fence_before();
@@ -195,31 +193,6 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int tap = 0; tap < P.taps; ++tap) tma_load_2d(&tm_w2, w_full, w2_base + tap * K::B_BYTES, 0, tap * P.w_rows_per_tap);
       const uint32_t a_bytes = static_cast<uint32_t>(P.slab_rows) * K::KROWB;
       Ring ra(P.sa);
-      if (stream_w2 && P.dual) {
-        // Two issuing threads AND a streamed W2: warp 3 issues conv2, so this thread feeds both rings.  Neither duty
-        // may block the other (the weight ring is shorter than one tile's taps), hence non-blocking probes.
-        Ring rb(P.rb);
-        int i = 0, tap = 0, wt = 0;   // next activation slab; next conv2 weight tap of tile wt
-        while (i < my_tiles || wt < my_tiles) {
-          bool progressed = false;
-          if (i < my_tiles && mbar_test_wait(&xa_empty[ra.idx], ra.phase ^ 1)) {
-            const int tile = blockIdx.x + i * gridDim.x;
-            mbar_expect_tx(&xa_full[ra.idx], a_bytes);
-            tma_load_2d(&tm_a, &xa_full[ra.idx], slab_base + ra.idx * P.slab_bytes, 0, tile * P.out_m - P.halo - P.pad);
-            ra.next();
-            ++i;
-            progressed = true;
-          }
-          if (wt < my_tiles && mbar_test_wait(&w2_empty[rb.idx], rb.phase ^ 1)) {
-            mbar_expect_tx(&w2_full[rb.idx], K::B_BYTES);
-            tma_load_2d(&tm_w2, &w2_full[rb.idx], w2_base + rb.idx * K::B_BYTES, 0, tap * P.w_rows_per_tap);
-            rb.next();
-            if (++tap == P.taps) { tap = 0; ++wt; }
-            progressed = true;
-          }
-          if (!progressed) __nanosleep(64);
-        }
-      } else
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
         mbar_wait(&xa_empty[ra.idx], ra.phase ^ 1);
@@ -339,8 +312,8 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp == 3) {
-    if (stream_w2 && !P.dual) {
-      // ===================== conv2 weight ring (W2 not resident, single issuer: warp 1 issues both convolutions) =====================
+    if (stream_w2) {
+      // ===================== conv2 weight ring (W2 not resident: warp 1 issues both convolutions) =====================
       if (elect_one()) {
         Ring rb(P.rb);
         for (int i = 0; i < my_tiles; ++i)
@@ -351,7 +324,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             rb.next();
           }
       }
-    } else if (warp == 3 && P.dual && elect_one()) {
+    } else if (P.dual && elect_one()) {
       // ===================== second MMA issuer: every conv2 phase (W2 resident) =====================
       // While one issuing thread is between phases (commit, mbarrier polls, fence, descriptor set-up: ~190 clk with a
       // 1-2 deep issue queue) the other one's MMAs keep the tensor pipe busy; the two only meet on the pipe itself.
@@ -424,14 +397,8 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       // issue slots from the warps doing the math: 20 warps share 4 schedulers)
       if (!P.leader_poll || lane_group == grp) {
         mbar_wait(&T_full[tbuf], tphase);
-        // One t slab shared by both groups and conv1 running ahead of conv2 (two issuers): the 1-bit phase of t_empty
-        // cannot tell "conv2 of tile i-1 committed" from the completion two tiles back, so the group of tile i only
-        // looks at t_empty after the group of tile i-1 got past its own wait (by then i-1 completions exist for sure)
-        const bool turns = P.nt == 1 && P.dual;
-        if (turns && i > 0) mbar_wait(e1_turn, static_cast<uint32_t>(i - 1) & 1);
         // t slab free: conv2 of the tile that used it last has been committed (nt == 1: the previous tile, i-1)
         mbar_wait(&t_empty[tb], ((P.nt == 2 ? n_done : static_cast<uint32_t>(i)) & 1) ^ 1);
-        if (turns && lane == 0 && (!P.leader_poll ? lane_group == 0 : true)) mbar_arrive(e1_turn);
       }
       if (P.leader_poll) named_bar_sync(1 + grp, 128);
       if (lane_group == 0 && lane == 0) PT(2, 0, i);
@@ -645,8 +612,7 @@ int launch_pair(const MrfPairProblem& p, cudaStream_t stream) {
   if (force_sa > 1 && force_sa < sa) sa = force_sa;
   kp.sa = sa;
   static const int env_dual = getenv("JATTS_B200_PAIR_DUAL") ? atoi(getenv("JATTS_B200_PAIR_DUAL")) : 1;
-  static const int env_dual_s = getenv("JATTS_B200_PAIR_DUAL_STREAM") ? atoi(getenv("JATTS_B200_PAIR_DUAL_STREAM")) : 1;
-  kp.dual = (env_dual && (rb == 0 || env_dual_s)) ? 1 : 0;   // streamed W2: the activation producer also feeds the weight ring
+  kp.dual = (env_dual && rb == 0) ? 1 : 0;   // with a streamed W2 warp 3 is the weight producer: single issuer
   static const int env_la = getenv("JATTS_B200_PAIR_LA") ? atoi(getenv("JATTS_B200_PAIR_LA")) : 0;
   // a slab is held from its load until the tile's store, so la + 1 tiles are in use when conv1 of the next one
   // needs its slab: la <= sa - 2 (more would deadlock the producer against the store)
