@@ -44,7 +44,7 @@ constexpr int kVBlock = 64 * 128;             // [64 keys x 64 dims] 8 KB
 constexpr int kVStage = 2 * kMaxNC * kVBlock; // hi blocks then lo blocks: 48 KB
 constexpr int kStgPitch = 20;                // staging row pitch in words: 16 data + 4 pad (conflict-free 128-bit rows)
 constexpr int kStgBytes = 32 * kStgPitch * 4;   // one worker warp's [32 rows x 16 words] transpose buffer
-constexpr int kSmemBytes = kRegionX + kRegionY + 1024 /*barriers*/ + 8 * kStgBytes + 1024 /*alignment*/;
+constexpr int kSmemBytes = kRegionX + kRegionY + 1024 /*barriers*/ + 8 * kStgBytes + 1024 /*row statistics*/ + 1024 /*alignment*/;
 static_assert(2 * kVStage <= kRegionY && 2 * kStageB <= kRegionX, "phase-3 buffers alias the phase-1/2 regions");
 
 struct AttParams {
@@ -131,6 +131,8 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
   uint64_t* v_empty = bars + 21;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
   uint8_t* stg_base = Y + kRegionY + 1024;   // [8 worker warps][kStgBytes]
+  float* stat_m = reinterpret_cast<float*>(stg_base + 8 * kStgBytes);   // [128] row maximum (log2 domain)
+  float* stat_l = stat_m + 128;                                         // [128] 1 / row sum (0 = row not owned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -370,8 +372,9 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
       if (tr4) ATR(25, it);
       // ---- softmax statistics: 16 rows per warp, two rows x 8 column blocks of loads in flight per lane; the
       //      combined score (log2 domain) replaces AC in place; max / sum are online across 256-column chunks only
-      float mrow[16], lrow[16];
-#pragma unroll
+      // (the row-pair loop is ROLLED and its results go through shared memory: unrolled 8x it was 4 k instructions, and
+      //  the warp-specialised kernels are instruction-cache sensitive)
+#pragma unroll 1
       for (int rp = 0; rp < 8; ++rp) {
         float M[2], L[2];
         float* pac[2];
@@ -441,11 +444,19 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
         for (int q = 0; q < 2; ++q) {
           const float Mw = warp_max(M[q]);
           const float Lw = warp_sum(M[q] > -INFINITY ? L[q] * ex2_approx(M[q] - Mw) : 0.f);
-          mrow[rp * 2 + q] = Lw > 0.f ? Mw : 0.f;          // rows this tile does not own have no scores:
-          lrow[rp * 2 + q] = Lw > 0.f ? 1.0f / Lw : 0.f;   // probability 0 (2^(-inf - 0) * 0)
+          if (lane == 0) {
+            stat_m[w * 16 + rp * 2 + q] = Lw > 0.f ? Mw : 0.f;          // rows this tile does not own have no scores:
+            stat_l[w * 16 + rp * 2 + q] = Lw > 0.f ? 1.0f / Lw : 0.f;   // probability 0 (2^(-inf - 0) * 0)
+          }
         }
       }
-      __syncwarp();   // the in-place scores of a row are read below by other lanes of this warp
+      __syncwarp();   // the in-place scores and the statistics of a row are read below by other lanes of this warp
+      float mrow[16], lrow[16];
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        mrow[rr] = stat_m[w * 16 + rr];
+        lrow[rr] = stat_l[w * 16 + rr];
+      }
       if (tr0) ATR(20, it);
       if (tr4) ATR(26, it);
       // ---- phase 3: probabilities of 64 keys -> (hi, lo') A-operand chunk (lane = 2 adjacent keys of 16 rows);

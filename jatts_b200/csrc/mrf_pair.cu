@@ -74,10 +74,14 @@ struct PairParams {
   float b1[64], b2[64];   // debug: clock64 timeline of CTA 0 (jatts_debug_set_trace), else null
 };
 
+#ifdef JB_PAIR_TRACE
 #define PT(role, ev, idx)                                                                                      \
   do {                                                                                                         \
     if (P.trace && blockIdx.x == 0 && (idx) < 64) P.trace[((role) * 8 + (ev)) * 64 + (idx)] = clock64();       \
   } while (0)
+#else
+#define PT(role, ev, idx) do { } while (0)   // the ~40 stamp sites cost ~300 instructions of a cache-sensitive kernel
+#endif
 
 struct Ring {
   int idx, depth;
@@ -235,7 +239,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint32_t a_lo0 = desc_lo0 + (a0 >> 4);
             const uint32_t b_lo0 = desc_lo0 + (w1_addr >> 4);
             const uint32_t a_step = (static_cast<uint32_t>(P.dil) * K::KROWB) >> 4;
-#pragma unroll
+#pragma unroll 1
             for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
               for (int k = 0; k < K::KSTEPS; ++k)
@@ -258,7 +262,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(4 * C + b * C);
           const uint32_t a0 = t_addr + static_cast<uint32_t>(rt.idx * K::T_BYTES);
-#pragma unroll
+#pragma unroll 1
           for (int tap = 0; tap < TAPS; ++tap) {
             uint32_t b_addr;
             if (stream_w2) {
@@ -345,7 +349,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(4 * C + b * C);
         const uint32_t a0 = t_addr + static_cast<uint32_t>(rt.idx * K::T_BYTES);
-#pragma unroll
+#pragma unroll 1
         for (int tap = 0; tap < TAPS; ++tap) {
           uint32_t b_addr;
           if (stream_w2) {
@@ -405,7 +409,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (lane_group == 0 && lane == 0) PT(2, 1, i);
       tc_fence_after();
       const uint32_t trow = smem_u32(t_base + tb * K::T_BYTES) + row_off;
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < C / 32; ++s) {
         uint32_t r[32];
         if (P.dbg < 2) {
@@ -481,7 +485,7 @@ mrf_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (lane_group == 0 && lane == 0) PT(3, 0, i);
       tc_fence_after();
       const uint32_t srow_p = smem_u32(slab_base + ra.idx * P.slab_bytes) + row_off;
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < C / 32; ++s) {
         uint32_t r[32];
         if (P.dbg < 2) {

@@ -62,8 +62,10 @@ __device__ __forceinline__ uint64_t global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// The poll loop with its timer / printf / trap is kept OUT of line: inlined at ~25 call sites it added ~750 instructions
+// per kernel, and the warp-specialised kernels are instruction-cache sensitive (mrf_pair_kernel<32, 11> ran 2.2x slower
+// when its code grew from 62 to 72 KB).
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -78,6 +80,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(

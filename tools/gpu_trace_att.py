@@ -25,6 +25,15 @@ a = _lib.RelposAttentionArgs(d_x_hi=xh.data_ptr(), d_x_lo=xl.data_ptr(), x_rows=
                              max_len=T, d_out_hi=oh.data_ptr(), d_out_lo=ol.data_ptr(), out_ld=D)
 st = torch.cuda.current_stream().cuda_stream
 _lib.check(_lib.lib.jatts_op_relpos_attention(C.byref(a), st))
+best = 1e9
+for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(_lib.lib.jatts_op_relpos_attention(C.byref(a), st))
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1))
+print(f"T={T} B={B}: best of 5 = {best * 1e3:.1f} us (op entry incl. scratch allocation)")
 trace = torch.zeros(5 * 8 * 64, dtype=torch.int64, device=dev)
 _lib.lib.jatts_debug_set_trace(trace.data_ptr())
 _lib.check(_lib.lib.jatts_op_relpos_attention(C.byref(a), st))
