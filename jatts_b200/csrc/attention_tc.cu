@@ -61,10 +61,14 @@ struct AttParams {
   long long* trace;  // debug: clock64 stamps of CTA 0 (jatts_debug_set_trace), else null
 };
 
+#ifdef JB_ENABLE_TRACE
 #define ATR(slot, idx)                                                                                       \
   do {                                                                                                       \
     if (P.trace && blockIdx.x == 0 && (idx) < 8) P.trace[(slot) * 8 + (idx)] = clock64();                    \
   } while (0)
+#else
+#define ATR(slot, idx) do { } while (0)
+#endif
 
 struct TileInfo {
   int h, a0, T, seg0;

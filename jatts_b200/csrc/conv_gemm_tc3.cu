@@ -80,10 +80,14 @@ struct Params3 {
   long long* trace;
 };
 
+#ifdef JB_ENABLE_TRACE
 #define JB_TRACE3(role, ev, idx)                                                                         \
   do {                                                                                                   \
     if (P.trace && blockIdx.x == 0 && (idx) < 64) P.trace[((role) * 8 + (ev)) * 64 + (idx)] = clock64(); \
   } while (0)
+#else
+#define JB_TRACE3(role, ev, idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t desc128(uint32_t smem_addr) {  // K-major, 128-byte swizzle
   uint64_t d = 0;

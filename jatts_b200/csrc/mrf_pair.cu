@@ -74,7 +74,7 @@ struct PairParams {
   float b1[64], b2[64];   // debug: clock64 timeline of CTA 0 (jatts_debug_set_trace), else null
 };
 
-#ifdef JB_PAIR_TRACE
+#ifdef JB_ENABLE_TRACE
 #define PT(role, ev, idx)                                                                                      \
   do {                                                                                                         \
     if (P.trace && blockIdx.x == 0 && (idx) < 64) P.trace[((role) * 8 + (ev)) * 64 + (idx)] = clock64();       \
