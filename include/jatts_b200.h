@@ -105,6 +105,36 @@ JATTS_API int jatts_fs2_plan(jatts_fs2* h, const int64_t* d_tokens, const int32_
 JATTS_API int jatts_fs2_run(jatts_fs2* h, float* d_mel, int64_t* d_durations, float* d_pitch, float* d_energy,
                   int32_t* d_lr_index, void* stream);
 
+/* ---- Matcha-TTS (replaces jatts/models/matchatts.py:390-560 on the inference path; BASELINE config 5) ---------
+ * Text side = the FastSpeech2 encoder / duration predictor / LengthRegulator (`text`: idim, odim, adim, aheads, elayers,
+ * eunits, ffn_kernel, enc_cnn_kernel, dur_*, spk_embed_dim, max_len are used, the remaining fields only have to be valid);
+ * decoder = the conditional-flow-matching U-Net of jatts/modules/matchatts/{flow_matching,decoder,transformer}.py. */
+typedef struct jatts_matcha jatts_matcha;
+typedef struct {
+  jatts_fs2_config text;
+  int32_t n_channels;                       /* len(decoder_channels): 2 */
+  int32_t channels[4];                      /* decoder_channels */
+  int32_t n_blocks, n_mid_blocks;           /* decoder_n_blocks, decoder_num_mid_blocks */
+  int32_t n_heads, head_dim;                /* decoder_num_heads, decoder_attention_head_dim */
+} jatts_matcha_config;
+JATTS_API int jatts_matcha_create(const jatts_matcha_config* cfg, const jatts_tensor* weights, int32_t n_weights,
+                        jatts_matcha** out);
+JATTS_API void jatts_matcha_destroy(jatts_matcha* h);
+/* ResnetBlock1D count of the decoder (2 down + mid + 2 up): the second dimension of the time-embedding table below */
+JATTS_API int32_t jatts_matcha_n_resnets(const jatts_matcha* h);
+/* Phase 1: encoder + duration predictor (matchatts.py:404-427).  h_n_frames[n_utt] (host) receives the number of mel
+ * frames of every utterance AFTER the truncation to an even length of matchatts.py:453-455. */
+JATTS_API int jatts_matcha_plan(jatts_matcha* h, const int64_t* d_tokens, const int32_t* h_text_lens, int32_t n_utt,
+                      const float* d_spembs, int32_t* h_n_frames, void* stream);
+/* Phase 2: LengthRegulator + encoder_proj + n_steps fixed Euler steps of the flow-matching decoder
+ * (flow_matching.py:48-95).  d_noise: fp32 [sum frames, odim] standard-normal z (the reference draws it with
+ * torch.randn_like inside CFM.inference; the caller draws it so that a run is reproducible), scaled by `temperature`.
+ * d_temb: fp32 [n_steps, n_resnets, C]: mlp_r(mish(time_mlp(sinusoid(t_step)))) of every ResnetBlock1D (decoder.py:91,
+ * :421-422): depends on the step only.  h_dt: host float[n_steps] step widths.  Outputs: d_mel fp32 [sum frames, odim],
+ * d_durations int64 [sum text]. */
+JATTS_API int jatts_matcha_run(jatts_matcha* h, const float* d_noise, float temperature, const float* d_temb,
+                     const float* h_dt, int32_t n_steps, float* d_mel, int64_t* d_durations, void* stream);
+
 /* ---- HiFi-GAN generator (replaces parallel_wavegan HiFiGANGenerator.inference behind vocoder.py:64) */
 typedef struct {
   int32_t in_channels, out_channels, channels, kernel_size;

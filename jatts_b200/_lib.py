@@ -29,6 +29,11 @@ class Fs2Config(C.Structure):
         "postnet_layers", "postnet_chans", "postnet_filts", "spk_embed_dim", "max_len")]
 
 
+class MatchaConfig(C.Structure):
+    _fields_ = [("text", Fs2Config), ("n_channels", C.c_int32), ("channels", C.c_int32 * 4), ("n_blocks", C.c_int32),
+                ("n_mid_blocks", C.c_int32), ("n_heads", C.c_int32), ("head_dim", C.c_int32)]
+
+
 class HifiganConfig(C.Structure):
     _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("channels", C.c_int32),
                 ("kernel_size", C.c_int32), ("n_upsamples", C.c_int32), ("upsample_scales", C.c_int32 * 8),
@@ -81,6 +86,7 @@ class RelposAttentionArgs(C.Structure):
 EXPORTS = (
     "jatts_abi_version", "jatts_last_error", "jatts_launch_count",
     "jatts_fs2_create", "jatts_fs2_destroy", "jatts_fs2_plan", "jatts_fs2_run",
+    "jatts_matcha_create", "jatts_matcha_destroy", "jatts_matcha_n_resnets", "jatts_matcha_plan", "jatts_matcha_run",
     "jatts_hifigan_create", "jatts_hifigan_destroy", "jatts_hifigan_run", "jatts_hifigan_run_pcm16", "jatts_op_conv_gemm", "jatts_op_mrf_pair",
     "jatts_op_relpos_attention",
     "jatts_profile_begin", "jatts_profile_end", "jatts_profile_end_classes", "jatts_debug_set_trace",
@@ -102,6 +108,15 @@ def _load():
     lib.jatts_fs2_plan.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
                                    C.c_float, C.POINTER(C.c_int32), C.c_void_p]
     lib.jatts_fs2_run.argtypes = [C.c_void_p] * 7
+    lib.jatts_matcha_create.argtypes = [C.POINTER(MatchaConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(C.c_void_p)]
+    lib.jatts_matcha_destroy.argtypes = [C.c_void_p]
+    lib.jatts_matcha_destroy.restype = None
+    lib.jatts_matcha_n_resnets.argtypes = [C.c_void_p]
+    lib.jatts_matcha_n_resnets.restype = C.c_int32
+    lib.jatts_matcha_plan.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
+                                      C.POINTER(C.c_int32), C.c_void_p]
+    lib.jatts_matcha_run.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_float), C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
     lib.jatts_hifigan_create.argtypes = [C.POINTER(HifiganConfig), C.POINTER(Tensor), C.c_int32,
                                          C.POINTER(C.c_void_p)]
     lib.jatts_hifigan_destroy.argtypes = [C.c_void_p]

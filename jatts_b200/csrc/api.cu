@@ -57,10 +57,16 @@ extern "C" int jatts_op_relpos_attention(const jatts_relpos_attention_args* a, v
   const size_t bytes = relpos_attention_scratch_bytes(a->max_len, a->nseg, a->n_head);
   float* scratch = nullptr;   // the engine keeps its scratch; the test entry allocates one per call
   if (bytes) JB_CUDA_OK(cudaMalloc(&scratch, bytes));
-  const int rc = relpos_attention(static_cast<const bf16*>(a->d_x_hi), static_cast<const bf16*>(a->d_x_lo), a->x_rows,
-                                  static_cast<const bf16*>(a->d_pos_hi), static_cast<const bf16*>(a->d_pos_lo), a->pos_rows,
-                                  a->n_head, a->d_model, L, a->max_len, scratch, bytes, static_cast<bf16*>(a->d_out_hi),
-                                  static_cast<bf16*>(a->d_out_lo), a->out_ld, s);
+  int rc;
+  if (a->d_pos_hi == nullptr && a->d_pos_lo == nullptr)   // plain attention: x = [q | k | v]
+    rc = plain_attention(static_cast<const bf16*>(a->d_x_hi), static_cast<const bf16*>(a->d_x_lo), a->x_rows, a->n_head,
+                         a->d_model, L, a->max_len, scratch, bytes, static_cast<bf16*>(a->d_out_hi),
+                         static_cast<bf16*>(a->d_out_lo), a->out_ld, s);
+  else
+    rc = relpos_attention(static_cast<const bf16*>(a->d_x_hi), static_cast<const bf16*>(a->d_x_lo), a->x_rows,
+                          static_cast<const bf16*>(a->d_pos_hi), static_cast<const bf16*>(a->d_pos_lo), a->pos_rows,
+                          a->n_head, a->d_model, L, a->max_len, scratch, bytes, static_cast<bf16*>(a->d_out_hi),
+                          static_cast<bf16*>(a->d_out_lo), a->out_ld, s);
   const cudaError_t e = cudaStreamSynchronize(s);
   if (scratch) cudaFree(scratch);
   if (rc == 0 && e != cudaSuccess) {

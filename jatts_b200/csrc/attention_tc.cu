@@ -21,6 +21,10 @@
 // No (B, H, T, T) tensor exists in HBM beyond the per-CTA scratch, no length limit below the positional table, and no
 // other attention kernel behind it: an unsupported head size is an error at engine creation.
 //
+// The same kernel runs plain scaled-dot-product attention (the Matcha decoder's transformer blocks, diffusers
+// `Attention` as configured by jatts/modules/matchatts/transformer.py:216-232): nph = 1 skips phase 2 and the
+// positional term of the index map; the projection matrix is then [q | k | v].
+//
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-9 = workers
 // (score epilogue: the four whose warp-id % 4 covers the TMEM lane quadrants; softmax and the P operand: all eight).
 #include "../../include/jatts_b200.h"
@@ -36,21 +40,28 @@ constexpr int kAttThreads = 320;
 constexpr int kOwnRows = 127;                 // rows a tile stores (row 127 only supplies BD[a+1])
 constexpr int kTile16 = 128 * 128;            // one [128 rows x 64 cols] 16-bit tile, 128-byte swizzled: 16 KB
 constexpr int kStageB = 2 * kTile16;          // hi + lo
-constexpr int kRingB = 3;
-constexpr int kMaxNC = 3;                     // d_k <= 192
-constexpr int kRegionX = kMaxNC * kStageB;    // Q (one stage per 64-wide d_k chunk); later the two P chunk buffers
-constexpr int kRegionY = kRingB * kStageB;    // K / position ring; later the two V stages
+constexpr int kMaxRing = 3;
+constexpr int kMaxNC = 4;                     // d_k <= 256
+// Operand region: 6 stages of 32 KB.  Phases 1 / 2: Q (one stage per 64-wide d_k chunk) followed by the K / position
+// ring (3 stages for d_k <= 192, 2 for d_k = 256).  Phase 3 aliases it: the two P chunk buffers, then the two V stages.
+constexpr int kRegion = 6 * kStageB;
 constexpr int kVBlock = 64 * 128;             // [64 keys x 64 dims] 8 KB
-constexpr int kVStage = 2 * kMaxNC * kVBlock; // hi blocks then lo blocks: 48 KB
 constexpr int kStgPitch = 20;                // staging row pitch in words: 16 data + 4 pad (conflict-free 128-bit rows)
 constexpr int kStgBytes = 32 * kStgPitch * 4;   // one worker warp's [32 rows x 16 words] transpose buffer
-constexpr int kSmemBytes = kRegionX + kRegionY + 1024 /*barriers*/ + 8 * kStgBytes + 1024 /*row statistics*/ + 1024 /*alignment*/;
-static_assert(2 * kVStage <= kRegionY && 2 * kStageB <= kRegionX, "phase-3 buffers alias the phase-1/2 regions");
+constexpr int kSmemBytes = kRegion + 1024 /*barriers*/ + 8 * kStgBytes + 1024 /*row statistics*/ + 1024 /*alignment*/;
+static_assert(2 * kStageB + 2 * 2 * kMaxNC * kVBlock <= kRegion, "phase-3 buffers alias the phase-1/2 region");
 
 struct AttParams {
   const int* seg_start;
   const int* seg_len;
-  int n_head, dk, nc, d_model;
+  int n_head, dk, nc;
+  int nph;           // 2: content + positional scores (legacy rel-pos attention); 1: content scores only (plain attention)
+  int q_col[2];      // first column of (q + bias_u), (q + bias_v) in the projection matrix; k_col / v_col likewise
+  int k_col, v_col;
+  int y_off;         // byte offset of the K / position ring inside the operand region (= size of the Q stages)
+  int ring;          // ring stages (2 or 3)
+  int v_off;         // byte offset of the two V stages (behind the two P chunk buffers)
+  int v_stage;       // bytes per V stage: 2 * nc * kVBlock
   int tiles_per_utt, total_tiles;
   int tp;            // scratch row pitch in floats (multiple of 128)
   float* scratch;    // [gridDim.x][2][128][tp]
@@ -118,8 +129,9 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* X = smem;
-  uint8_t* Y = smem + kRegionX;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Y + kRegionY);
+  uint8_t* Y = smem + P.y_off;
+  uint8_t* V = smem + P.v_off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRegion);
   uint64_t* q_full = bars + 0;
   uint64_t* q_free = bars + 1;
   uint64_t* s2_done = bars + 2;
@@ -134,7 +146,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
   uint64_t* v_full = bars + 19;    // [2]
   uint64_t* v_empty = bars + 21;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
-  uint8_t* stg_base = Y + kRegionY + 1024;   // [8 worker warps][kStgBytes]
+  uint8_t* stg_base = smem + kRegion + 1024;   // [8 worker warps][kStgBytes]
   float* stat_m = reinterpret_cast<float*>(stg_base + 8 * kStgBytes);   // [128] row maximum (log2 domain)
   float* stat_l = stat_m + 128;                                         // [128] 1 / row sum (0 = row not owned)
 
@@ -147,7 +159,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
     tma_prefetch_desc(&tm_p_hi); tma_prefetch_desc(&tm_p_lo);
     mbar_init(q_full, 1); mbar_init(q_free, 1); mbar_init(s2_done, 1); mbar_init(ctx_full, 1);
     mbar_init(tile_free, 8);
-    for (int i = 0; i < kRingB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < kMaxRing; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
       mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
@@ -166,7 +178,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
   pdl_launch_dependents();
   pdl_wait();   // the projection GEMM's outputs are visible from here
 
-  const int D = P.d_model;
+  const uint32_t ring = static_cast<uint32_t>(P.ring);
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (elect_one()) {
@@ -181,14 +193,14 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
         auto load_q = [&](int which) {
           mbar_expect_tx(q_full, static_cast<uint32_t>(P.nc) * kStageB);
           for (int c = 0; c < P.nc; ++c) {
-            tma_load_2d(&tm_x_hi, q_full, X + c * kStageB, which * D + hcol + c * 64, ti.seg0 + ti.a0);
-            tma_load_2d(&tm_x_lo, q_full, X + c * kStageB + kTile16, which * D + hcol + c * 64, ti.seg0 + ti.a0);
+            tma_load_2d(&tm_x_hi, q_full, X + c * kStageB, P.q_col[which] + hcol + c * 64, ti.seg0 + ti.a0);
+            tma_load_2d(&tm_x_lo, q_full, X + c * kStageB + kTile16, P.q_col[which] + hcol + c * 64, ti.seg0 + ti.a0);
           }
         };
         auto load_b = [&](const CUtensorMap* mh, const CUtensorMap* ml, int col0, int row) {
           for (int c = 0; c < P.nc; ++c) {
-            const uint32_t st = nb % kRingB;
-            mbar_wait(&b_empty[st], ((nb / kRingB) & 1) ^ 1);
+            const uint32_t st = nb % ring;
+            mbar_wait(&b_empty[st], ((nb / ring) & 1) ^ 1);
             mbar_expect_tx(&b_full[st], kStageB);
             tma_load_2d(mh, &b_full[st], Y + st * kStageB, col0 + c * 64, row);
             tma_load_2d(ml, &b_full[st], Y + st * kStageB + kTile16, col0 + c * 64, row);
@@ -196,21 +208,23 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
           }
         };
         load_q(0);                                                                         // q + bias_u
-        for (int j = 0; j < nkt; ++j) load_b(&tm_x_hi, &tm_x_lo, 2 * D + hcol, ti.seg0 + j * 128);   // keys
+        for (int j = 0; j < nkt; ++j) load_b(&tm_x_hi, &tm_x_lo, P.k_col + hcol, ti.seg0 + j * 128);   // keys
         ATR(1, it);
-        mbar_wait(q_free, it & 1);                                                         // phase-1 MMAs done with Q
-        ATR(2, it);
-        load_q(1);                                                                         // q + bias_v
-        for (int j = 0; j < nkt; ++j) load_b(&tm_p_hi, &tm_p_lo, hcol, j * 128);           // positions 0 .. T-1
+        if (P.nph == 2) {
+          mbar_wait(q_free, it & 1);                                                       // phase-1 MMAs done with Q
+          ATR(2, it);
+          load_q(1);                                                                       // q + bias_v
+          for (int j = 0; j < nkt; ++j) load_b(&tm_p_hi, &tm_p_lo, hcol, j * 128);         // positions 0 .. T-1
+        }
         mbar_wait(s2_done, it & 1);                                                        // ring and Q regions are free
         ATR(3, it);
         for (int kc = 0; kc < nkc; ++kc) {
           const uint32_t st = nv & 1;
           mbar_wait(&v_empty[st], ((nv >> 1) & 1) ^ 1);
-          mbar_expect_tx(&v_full[st], static_cast<uint32_t>(2 * P.nc) * kVBlock);
+          mbar_expect_tx(&v_full[st], static_cast<uint32_t>(P.v_stage));
           for (int c = 0; c < P.nc; ++c) {
-            tma_load_2d(&tm_v_hi, &v_full[st], Y + st * kVStage + c * kVBlock, 3 * D + hcol + c * 64, ti.seg0 + kc * 64);
-            tma_load_2d(&tm_v_lo, &v_full[st], Y + st * kVStage + (P.nc + c) * kVBlock, 3 * D + hcol + c * 64, ti.seg0 + kc * 64);
+            tma_load_2d(&tm_v_hi, &v_full[st], V + st * P.v_stage + c * kVBlock, P.v_col + hcol + c * 64, ti.seg0 + kc * 64);
+            tma_load_2d(&tm_v_lo, &v_full[st], V + st * P.v_stage + (P.nc + c) * kVBlock, P.v_col + hcol + c * 64, ti.seg0 + kc * 64);
           }
           ++nv;
         }
@@ -225,7 +239,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
       constexpr uint32_t desc_hi = static_cast<uint32_t>(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, v1, SWIZZLE_128B
       constexpr uint32_t k_lo0 = 1u << 16;                                      // K-major: LBO unused
       constexpr uint32_t v_lo0 = static_cast<uint32_t>(kVBlock >> 4) << 16;     // MN-major: LBO = next 64-wide block of d
-      const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y);
+      const uint32_t x_addr = smem_u32(X), y_addr = smem_u32(Y), v_addr = smem_u32(V);
       uint32_t nb = 0, nv = 0, sb = 0, pc = 0, qf = 0, it = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileInfo ti = decode_tile(P, tile);
@@ -234,7 +248,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
         if (it > 0) mbar_wait(tile_free, (it - 1) & 1);   // the context accumulators of the previous tile were read
         tc_fence_after();
         ATR(8, it);
-        for (int ph = 0; ph < 2; ++ph) {
+        for (int ph = 0; ph < P.nph; ++ph) {
           mbar_wait(q_full, qf & 1);
           ++qf;
           tc_fence_after();
@@ -247,8 +261,8 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
             // the last key / position tile only computes the 16-column groups that hold real keys
             const uint32_t idesc_j = att_idesc(min(128, round_up(ti.T - j * 128, 16)), false);
             for (int c = 0; c < P.nc; ++c) {
-              const uint32_t st = nb % kRingB;
-              mbar_wait(&b_full[st], (nb / kRingB) & 1);
+              const uint32_t st = nb % ring;
+              mbar_wait(&b_full[st], (nb / ring) & 1);
               tc_fence_after();
               const uint32_t a0 = x_addr + c * kStageB, b0 = y_addr + st * kStageB;
 #pragma unroll
@@ -266,7 +280,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
             tc_commit(&s_full[buf]);
             ++sb;
           }
-          tc_commit(ph == 0 ? q_free : s2_done);
+          tc_commit(ph == P.nph - 1 ? s2_done : q_free);
           ATR(10 + 2 * ph, it);
         }
         for (int kc = 0; kc < nkc; ++kc) {
@@ -275,7 +289,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
           mbar_wait(&v_full[vs], (nv >> 1) & 1);
           tc_fence_after();
           if (kc == 0) ATR(13, it);
-          const uint32_t a0 = x_addr + pb * kStageB, b0 = y_addr + vs * kVStage;
+          const uint32_t a0 = x_addr + pb * kStageB, b0 = v_addr + vs * static_cast<uint32_t>(P.v_stage);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 16 keys per MMA: 32 B along the A rows, two 8-key groups (2 KB) of V
             const uint32_t ah = k_lo0 + ((a0 + k * 32) >> 4), al = k_lo0 + ((a0 + kTile16 + k * 32) >> 4);
@@ -313,6 +327,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
     const uint32_t stg_w = stg + static_cast<uint32_t>(lane * kStgPitch * 4);
     const uint32_t stg_r = stg + static_cast<uint32_t>(((lane >> 2) * kStgPitch + (lane & 3) * 4) * 4);
     const float sc2 = P.scale * 1.4426950408889634f;   // scores are kept in the log2 domain: p = 2^(s - max)
+    const bool pos = P.nph == 2;
     uint32_t se = 0, pc = 0, it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileInfo ti = decode_tile(P, tile);
@@ -322,7 +337,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
       const bool tr0 = warp == 2 && lane == 0, tr4 = warp == 6 && lane == 0;
       if (tr0) ATR(16, it);
       // ---- score epilogue: TMEM (main + corr * 2^-11) -> scratch; every warp moves 4 of the 8 16-column groups
-      for (int ph = 0; ph < 2; ++ph) {
+      for (int ph = 0; ph < P.nph; ++ph) {
         float* dst = scr + (static_cast<size_t>(ph) * 128 + quad * 32 + (lane >> 2)) * tp + hsel * 64 + (lane & 3) * 4;
         for (int j = 0; j < nkt; ++j) {
           const uint32_t buf = se & 1;
@@ -414,7 +429,7 @@ relpos_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __
                 const int b = min(c0 + 32 * i + lane, T - 1);
                 const float* pb = b <= aa[q] ? plo[q] : phi[q];
                 xv[q][i] = pac[q][b];
-                yv[q][i] = pb[b];
+                yv[q][i] = pos ? pb[b] : 0.f;
               }
 #pragma unroll
             for (int q = 0; q < 2; ++q)
@@ -572,15 +587,21 @@ size_t relpos_attention_scratch_bytes(int max_len, int nseg, int n_head) {
   return static_cast<size_t>(grid) * 2 * 128 * round_up(max_len, 128) * sizeof(float);
 }
 
-int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const bf16* pos_hi, const bf16* pos_lo,
-                     int pos_rows, int n_head, int d_model, RowLayout L, int max_len, float* scratch,
-                     size_t scratch_bytes, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s) {
+// x: [x_rows, x_ld] projection matrix (operand pairs); q_col0 / q_col1 / k_col / v_col: first column of each block.
+// pos_hi == null: plain softmax(q k^T / sqrt(d_k)) v (q_col1 unused).
+static int attention_launch(const bf16* x_hi, const bf16* x_lo, long long x_rows, int x_ld, int q_col0, int q_col1, int k_col,
+                            int v_col, const bf16* pos_hi, const bf16* pos_lo, int pos_rows, int n_head, int d_model,
+                            RowLayout L, int max_len, float* scratch, size_t scratch_bytes, bf16* out_hi, bf16* out_lo,
+                            int out_ld, cudaStream_t s) {
   JB_REQUIRE(relpos_attention_supported(n_head, d_model), JATTS_E_UNSUPPORTED,
-             "attention: d_k must be 64, 128 or 192 (tcgen05 kernel; there is no other attention path)");
-  JB_REQUIRE(x_hi && x_lo && pos_hi && pos_lo && out_hi && out_lo, JATTS_E_INVALID, "attention: null operand");
-  JB_REQUIRE(max_len <= pos_rows, JATTS_E_UNSUPPORTED, "attention: utterance longer than the positional table");
+             "attention: d_k must be 64, 128, 192 or 256 (tcgen05 kernel; there is no other attention path)");
+  JB_REQUIRE(x_hi && x_lo && out_hi && out_lo && (pos_hi != nullptr) == (pos_lo != nullptr), JATTS_E_INVALID, "attention: null operand");
+  const bool pos = pos_hi != nullptr;
+  JB_REQUIRE(!pos || max_len <= pos_rows, JATTS_E_UNSUPPORTED, "attention: utterance longer than the positional table");
   JB_REQUIRE(out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_lo) & 15) == 0,
              JATTS_E_INVALID, "attention: output rows must be 16-byte aligned");
+  JB_REQUIRE(x_ld % 8 == 0 && q_col0 % 8 == 0 && q_col1 % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0, JATTS_E_INVALID,
+             "attention: operand blocks must start on 16-byte boundaries");
   if (L.nseg == 0 || max_len == 0) return 0;
   JB_REQUIRE(scratch != nullptr && scratch_bytes >= relpos_attention_scratch_bytes(max_len, L.nseg, n_head), JATTS_E_INVALID,
              "attention: scratch buffer too small");
@@ -590,7 +611,14 @@ int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const
   P.n_head = n_head;
   P.dk = d_model / n_head;
   P.nc = P.dk / 64;
-  P.d_model = d_model;
+  P.nph = pos ? 2 : 1;
+  P.q_col[0] = q_col0; P.q_col[1] = q_col1; P.k_col = k_col; P.v_col = v_col;
+  P.y_off = (P.nc <= 3 ? 3 : 4) * kStageB;
+  P.ring = (kRegion - P.y_off) / kStageB;
+  P.v_stage = 2 * P.nc * kVBlock;
+  P.v_off = P.nc <= 3 ? P.y_off : 2 * kStageB;   // d_k = 256: the V stages start right behind the two P buffers
+  JB_REQUIRE(P.ring >= 2 && P.ring <= kMaxRing && P.v_off >= 2 * kStageB && P.v_off + 2 * P.v_stage <= kRegion, JATTS_E_UNSUPPORTED,
+             "attention: shared-memory plan");
   P.tiles_per_utt = ceil_div(max_len, kOwnRows);
   P.total_tiles = L.nseg * n_head * P.tiles_per_utt;
   P.tp = round_up(max_len, 128);
@@ -601,18 +629,37 @@ int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const
   P.scale = 1.0f / sqrtf(static_cast<float>(P.dk));
   P.trace = g_trace_ptr;
   CUtensorMap mxh, mxl, mvh, mvl, mph, mpl;
-  JB_PROPAGATE(make_tmap(&mxh, x_hi, x_rows, 4 * d_model, 4 * d_model, 128));
-  JB_PROPAGATE(make_tmap(&mxl, x_lo, x_rows, 4 * d_model, 4 * d_model, 128));
-  JB_PROPAGATE(make_tmap(&mvh, x_hi, x_rows, 4 * d_model, 4 * d_model, 64));
-  JB_PROPAGATE(make_tmap(&mvl, x_lo, x_rows, 4 * d_model, 4 * d_model, 64));
-  JB_PROPAGATE(make_tmap(&mph, pos_hi, pos_rows, d_model, d_model, 128));
-  JB_PROPAGATE(make_tmap(&mpl, pos_lo, pos_rows, d_model, d_model, 128));
+  JB_PROPAGATE(make_tmap(&mxh, x_hi, x_rows, x_ld, x_ld, 128));
+  JB_PROPAGATE(make_tmap(&mxl, x_lo, x_rows, x_ld, x_ld, 128));
+  JB_PROPAGATE(make_tmap(&mvh, x_hi, x_rows, x_ld, x_ld, 64));
+  JB_PROPAGATE(make_tmap(&mvl, x_lo, x_rows, x_ld, x_ld, 64));
+  if (pos) {
+    JB_PROPAGATE(make_tmap(&mph, pos_hi, pos_rows, d_model, d_model, 128));
+    JB_PROPAGATE(make_tmap(&mpl, pos_lo, pos_rows, d_model, d_model, 128));
+  } else {   // never dereferenced (nph == 1); a valid descriptor keeps the prefetch harmless
+    mph = mxh;
+    mpl = mxl;
+  }
   JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(relpos_attention_tc_kernel), kSmemBytes));
   const int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
   ProfileScope prof(s, PROF_ATTENTION);
   JB_CUDA_OK(launch_tc(relpos_attention_tc_kernel, grid, kAttThreads, kSmemBytes, s, 1, mxh, mxl, mvh, mvl, mph, mpl, P));
   JB_KERNEL_OK();
   return 0;
+}
+
+int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const bf16* pos_hi, const bf16* pos_lo,
+                     int pos_rows, int n_head, int d_model, RowLayout L, int max_len, float* scratch,
+                     size_t scratch_bytes, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s) {
+  JB_REQUIRE(pos_hi && pos_lo, JATTS_E_INVALID, "attention: null positional table");
+  return attention_launch(x_hi, x_lo, x_rows, 4 * d_model, 0, d_model, 2 * d_model, 3 * d_model, pos_hi, pos_lo, pos_rows,
+                          n_head, d_model, L, max_len, scratch, scratch_bytes, out_hi, out_lo, out_ld, s);
+}
+
+int plain_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, int n_head, int d_model, RowLayout L, int max_len,
+                    float* scratch, size_t scratch_bytes, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s) {
+  return attention_launch(x_hi, x_lo, x_rows, 3 * d_model, 0, 0, d_model, 2 * d_model, nullptr, nullptr, 0, n_head, d_model, L,
+                          max_len, scratch, scratch_bytes, out_hi, out_lo, out_ld, s);
 }
 
 }  // namespace jb

@@ -6,71 +6,9 @@
 // (3 MMAs per K step, fp32 TMEM accumulation); activations between kernels are fp32 masters plus the
 // hi/lo operand copies the next GEMM needs.  Attention core, LayerNorm, depthwise conv, predictors'
 // tails and the length regulator are fp32 CUDA-core kernels.
-#include <cmath>
-
-#include "engine_common.cuh"
-
-namespace jb {
-
-struct ConformerLayerW {
-  const float *ln_ffm_g, *ln_ffm_b, *ln_mha_g, *ln_mha_b, *ln_conv_g, *ln_conv_b, *ln_ff_g, *ln_ff_b, *ln_fin_g,
-      *ln_fin_b;
-  ConvW ffm_w1, ffm_w2, ff_w1, ff_w2, qkv, out, pw1, pw2;
-  const bf16 *pos_hi, *pos_lo;         // [max_len, D] fp16 (hi, lo*2^11) pair of linear_pos(pe); the biases u / v
-                                       // are folded into the projection GEMM (its two biased copies of q)
-  const float *dw_wT, *dw_b;           // BatchNorm folded
-  int dw_k;
-};
-struct ConformerW {
-  std::vector<ConformerLayerW> layers;
-  const float *after_g, *after_b;
-};
-struct PredictorW {
-  std::vector<ConvW> conv;
-  std::vector<const float*> ln_g, ln_b;
-  const float* lin_w;
-  float lin_b;
-  int chans;
-};
-
-}  // namespace jb
+#include "engine_fs2.cuh"
 
 using namespace jb;
-
-struct jatts_fs2 {
-  jatts_fs2_config cfg;
-  int device = 0;
-  WeightTable wt;
-  ConformerW enc, dec;
-  PredictorW dur, pitch, energy;
-  const float *emb, *pitch_w, *pitch_b, *energy_w, *energy_b, *spk_w, *spk_b;
-  ConvW feat_out;
-  std::vector<ConvW> postnet;
-
-  Arena arena;
-  int cap_rows = 0, cap_utt = 0;
-  // workspace views (valid after ensure_workspace)
-  float *x, *hs, *g, *pf, *before, *after, *s_dur, *s_pitch, *s_energy, *o_pitch, *o_energy;
-  bf16 *q4_hi, *q4_lo;   // [rows, 4*D] projection output: q + u | q + v | k | v as operand pairs
-  float* att_scratch = nullptr;   // per-CTA score rows of the attention kernel (own allocation, grown on demand)
-  size_t att_scratch_bytes = 0;
-  bf16 *h_hi, *h_lo, *t_hi, *t_lo, *c_hi, *c_lo, *p_hi, *p_lo, *b_hi, *b_lo, *pa_hi, *pa_lo, *pb_hi, *pb_lo;
-  long long* o_dur;
-  int *cum, *lr_index, *d_nframes;
-  uint8_t* mask;
-  int *seg, *d_small;  // d_small: [seg_start | seg_len | off] x 2 phases
-  int* h_small = nullptr;  // pinned staging, same shape
-  int* h_nframes = nullptr;
-
-  // state between plan and run
-  bool planned = false;
-  int n_utt = 0;
-  float alpha = 1.0f;
-  HostLayout text, frame;
-  RowLayout Lt, Lf;
-  const int* d_text_off = nullptr;
-  const int* d_frame_off = nullptr;
-};
 
 namespace jb {
 
@@ -128,7 +66,7 @@ static int load_predictor(const WeightTable& wt, const std::string& pre, int n_l
   return 0;
 }
 
-static RowLayout device_layout(const jatts_fs2* h, const HostLayout& hl, int phase) {
+RowLayout fs2_device_layout(const jatts_fs2* h, const HostLayout& hl, int phase) {
   RowLayout L;
   const int cu = h->cap_utt;
   const int* base = h->d_small + phase * 3 * cu;
@@ -153,7 +91,7 @@ static int upload_layout(jatts_fs2* h, const HostLayout& hl, int phase, cudaStre
   }
   int* db = h->d_small + phase * 3 * cu;
   JB_CUDA_OK(cudaMemcpyAsync(db, hb, sizeof(int) * 3 * cu, cudaMemcpyHostToDevice, s));
-  *L = device_layout(h, hl, phase);
+  *L = fs2_device_layout(h, hl, phase);
   *d_off = db + 2 * cu;
   JB_PROPAGATE(fill_layout(L->seg_start, L->seg_len, L->nseg, L->n_rows, h->mask, h->seg, s));
   return 0;
@@ -233,8 +171,8 @@ static int zero_operand_gaps(jatts_fs2* h, const RowLayout& L, cudaStream_t s) {
 }
 
 // out = epilogue(conv(A)) with "same" padding over the packed layout
-static int run_conv(const ConvW& w, const bf16* a_hi, const bf16* a_lo, int a_ld, const RowLayout& L,
-                    ConvGemmEpilogue ep, cudaStream_t s, int dilation = 1) {
+int split_conv(const ConvW& w, const bf16* a_hi, const bf16* a_lo, int a_ld, const RowLayout& L, ConvGemmEpilogue ep,
+               cudaStream_t s, int dilation) {
   ConvGemmProblem p{};
   p.a_hi = a_hi; p.a_lo = a_lo; p.a_rows = L.n_rows; p.a_ld = a_ld;
   p.w_hi = w.hi; p.w_lo = w.lo; p.taps = w.taps; p.n_pad = w.n_pad; p.k_pad = w.k_pad;
@@ -252,10 +190,10 @@ static int conv_ffn(jatts_fs2* h, const ConvW& w1, const ConvW& w2, const RowLay
   const int d = h->cfg.adim, u = w1.n;
   ConvGemmEpilogue e1{};  // Conv1d -> ReLU (multi_layer_conv.py:62)
   e1.act = ACT_RELU; e1.out_hi = h->t_hi; e1.out_lo = h->t_lo; e1.out_bf_ld = u;
-  JB_PROPAGATE(run_conv(w1, h->h_hi, h->h_lo, d, L, e1, s));
+  JB_PROPAGATE(split_conv(w1, h->h_hi, h->h_lo, d, L, e1, s));
   ConvGemmEpilogue e2{};  // x = residual + 0.5 * ffn (encoder_layer.py:114-120, ff_scale)
   e2.scale = 0.5f; e2.res_f32 = h->x; e2.res_ld = d; e2.out_f32 = h->x; e2.out_f32_ld = d;
-  JB_PROPAGATE(run_conv(w2, h->t_hi, h->t_lo, u, L, e2, s));
+  JB_PROPAGATE(split_conv(w2, h->t_hi, h->t_lo, u, L, e2, s));
   return 0;
 }
 
@@ -279,21 +217,21 @@ static int conformer_stack(jatts_fs2* h, const ConformerW& W, const RowLayout& L
     JB_PROPAGATE(layernorm_rows(h->x, d, Lw.ln_mha_g, Lw.ln_mha_b, eps, L, nullptr, h->h_hi, h->h_lo, d, s));
     ConvGemmEpilogue eq{};
     eq.out_hi = h->q4_hi; eq.out_lo = h->q4_lo; eq.out_bf_ld = 4 * d;
-    JB_PROPAGATE(run_conv(Lw.qkv, h->h_hi, h->h_lo, d, L, eq, s));
+    JB_PROPAGATE(split_conv(Lw.qkv, h->h_hi, h->h_lo, d, L, eq, s));
     JB_PROPAGATE(relpos_attention(h->q4_hi, h->q4_lo, h->cap_rows, Lw.pos_hi, Lw.pos_lo, c.max_len, c.aheads, d, L, max_len,
                                   h->att_scratch, h->att_scratch_bytes, h->c_hi, h->c_lo, d, s));
     ConvGemmEpilogue eo{};
     eo.res_f32 = h->x; eo.res_ld = d; eo.out_f32 = h->x; eo.out_f32_ld = d;
-    JB_PROPAGATE(run_conv(Lw.out, h->c_hi, h->c_lo, d, L, eo, s));
+    JB_PROPAGATE(split_conv(Lw.out, h->c_hi, h->c_lo, d, L, eo, s));
     // convolution module (encoder_layer.py:149-156, convolution.py:56-79)
     JB_PROPAGATE(layernorm_rows(h->x, d, Lw.ln_conv_g, Lw.ln_conv_b, eps, L, nullptr, h->h_hi, h->h_lo, d, s));
     ConvGemmEpilogue eg{};
     eg.act = ACT_GLU; eg.out_f32 = h->g; eg.out_f32_ld = d;
-    JB_PROPAGATE(run_conv(Lw.pw1, h->h_hi, h->h_lo, d, L, eg, s));
+    JB_PROPAGATE(split_conv(Lw.pw1, h->h_hi, h->h_lo, d, L, eg, s));
     JB_PROPAGATE(dwconv_swish(h->g, d, Lw.dw_wT, Lw.dw_b, Lw.dw_k, L, max_len, h->c_hi, h->c_lo, d, s));
     ConvGemmEpilogue e2{};
     e2.res_f32 = h->x; e2.res_ld = d; e2.out_f32 = h->x; e2.out_f32_ld = d;
-    JB_PROPAGATE(run_conv(Lw.pw2, h->c_hi, h->c_lo, d, L, e2, s));
+    JB_PROPAGATE(split_conv(Lw.pw2, h->c_hi, h->c_lo, d, L, e2, s));
     // FFN (encoder_layer.py:158-168) and the block's final norm (:170-171)
     JB_PROPAGATE(layernorm_rows(h->x, d, Lw.ln_ff_g, Lw.ln_ff_b, eps, L, nullptr, h->h_hi, h->h_lo, d, s));
     JB_PROPAGATE(conv_ffn(h, Lw.ff_w1, Lw.ff_w2, L, s));
@@ -310,8 +248,8 @@ static int predictor(jatts_fs2* h, const PredictorW& W, const RowLayout& L, floa
   for (int i = 0; i < n; ++i) {
     ConvGemmEpilogue e{};
     e.act = ACT_RELU; e.out_f32 = h->pf; e.out_f32_ld = W.chans;
-    if (i == 0) JB_PROPAGATE(run_conv(W.conv[i], h->h_hi, h->h_lo, d, L, e, s));
-    else JB_PROPAGATE(run_conv(W.conv[i], h->p_hi, h->p_lo, W.chans, L, e, s));
+    if (i == 0) JB_PROPAGATE(split_conv(W.conv[i], h->h_hi, h->h_lo, d, L, e, s));
+    else JB_PROPAGATE(split_conv(W.conv[i], h->p_hi, h->p_lo, W.chans, L, e, s));
     if (i + 1 < n)
       JB_PROPAGATE(layernorm_rows(h->pf, W.chans, W.ln_g[i], W.ln_b[i], eps, L, nullptr, h->p_hi, h->p_lo, W.chans, s));
     else
@@ -322,8 +260,9 @@ static int predictor(jatts_fs2* h, const PredictorW& W, const RowLayout& L, floa
 
 }  // namespace jb
 
-extern "C" int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor* weights, int32_t n_weights,
-                                jatts_fs2** out) {
+namespace jb {
+int fs2_create_impl(const jatts_fs2_config* cfg, const jatts_tensor* weights, int32_t n_weights, bool text_only,
+                    jatts_fs2** out) {
   JB_REQUIRE(cfg && weights && out, JATTS_E_INVALID, "fs2_create: null argument");
   JB_REQUIRE(cfg->adim % 64 == 0 && cfg->adim <= 512, JATTS_E_UNSUPPORTED, "adim must be a multiple of 64, <= 512");
   JB_REQUIRE(cfg->adim % cfg->aheads == 0, JATTS_E_INVALID, "adim % aheads");
@@ -333,9 +272,9 @@ extern "C" int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor*
   JB_REQUIRE(cfg->dur_chans % 64 == 0 && cfg->pitch_chans % 64 == 0 && cfg->energy_chans % 64 == 0 &&
                  cfg->dur_chans <= 512 && cfg->pitch_chans <= 512 && cfg->energy_chans <= 512,
              JATTS_E_UNSUPPORTED, "predictor channels must be multiples of 64, <= 512");
-  JB_REQUIRE(cfg->postnet_chans % 64 == 0 && cfg->postnet_layers >= 1, JATTS_E_UNSUPPORTED, "postnet channels % 64");
+  JB_REQUIRE(text_only || (cfg->postnet_chans % 64 == 0 && cfg->postnet_layers >= 1), JATTS_E_UNSUPPORTED, "postnet channels % 64");
   JB_REQUIRE(cfg->max_len > 0 && cfg->max_len <= 5000, JATTS_E_INVALID, "max_len must be in (0, 5000]");
-  JB_REQUIRE(cfg->dur_layers >= 1 && cfg->pitch_layers >= 1 && cfg->energy_layers >= 1, JATTS_E_UNSUPPORTED,
+  JB_REQUIRE(cfg->dur_layers >= 1 && (text_only || (cfg->pitch_layers >= 1 && cfg->energy_layers >= 1)), JATTS_E_UNSUPPORTED,
              "predictors need >= 1 layer");
   // "same" convolutions over the packed layout rely on the kGapRows zero rows between utterances: an even kernel
   // would be centred differently from the reference's padding=(k-1)//2 and a half width above the gap would read
@@ -347,6 +286,7 @@ extern "C" int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor*
              "conformer depthwise kernel sizes must be odd");
   jatts_fs2* h = new jatts_fs2();
   h->cfg = *cfg;
+  h->text_only = text_only;
   h->d_small = nullptr; h->d_nframes = nullptr;
   auto fail = [&](int rc) { delete h; return rc; };
   if (cudaGetDevice(&h->device) != cudaSuccess) { set_last_error("cudaGetDevice failed (no CUDA device?)"); return fail(JATTS_E_CUDA); }
@@ -354,19 +294,29 @@ extern "C" int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor*
   if (rc) return fail(rc);
   const int d = cfg->adim;
   if ((rc = load_conformer(h->wt, "enc", cfg->elayers, d, cfg->eunits, cfg->ffn_kernel, cfg->enc_cnn_kernel, cfg->max_len, cfg->aheads, &h->enc))) return fail(rc);
+  if (!text_only)
   if ((rc = load_conformer(h->wt, "dec", cfg->dlayers, d, cfg->dunits, cfg->ffn_kernel, cfg->dec_cnn_kernel, cfg->max_len, cfg->aheads, &h->dec))) return fail(rc);
   if ((rc = load_predictor(h->wt, "dur", cfg->dur_layers, cfg->dur_chans, cfg->dur_kernel, d, &h->dur))) return fail(rc);
+  if (!text_only)
   if ((rc = load_predictor(h->wt, "pitch", cfg->pitch_layers, cfg->pitch_chans, cfg->pitch_kernel, d, &h->pitch))) return fail(rc);
+  if (!text_only)
   if ((rc = load_predictor(h->wt, "energy", cfg->energy_layers, cfg->energy_chans, cfg->energy_kernel, d, &h->energy))) return fail(rc);
   if ((rc = h->wt.f32("emb", static_cast<long long>(cfg->idim) * d, &h->emb))) return fail(rc);
-  if ((rc = h->wt.f32("pitch_embed.w", d, &h->pitch_w))) return fail(rc);
-  if ((rc = h->wt.f32("pitch_embed.b", d, &h->pitch_b))) return fail(rc);
-  if ((rc = h->wt.f32("energy_embed.w", d, &h->energy_w))) return fail(rc);
-  if ((rc = h->wt.f32("energy_embed.b", d, &h->energy_b))) return fail(rc);
+  h->pitch_w = h->pitch_b = h->energy_w = h->energy_b = nullptr;
+  if (!text_only) {
+    if ((rc = h->wt.f32("pitch_embed.w", d, &h->pitch_w))) return fail(rc);
+    if ((rc = h->wt.f32("pitch_embed.b", d, &h->pitch_b))) return fail(rc);
+    if ((rc = h->wt.f32("energy_embed.w", d, &h->energy_w))) return fail(rc);
+    if ((rc = h->wt.f32("energy_embed.b", d, &h->energy_b))) return fail(rc);
+  }
   h->spk_w = h->spk_b = nullptr;
   if (cfg->spk_embed_dim > 0) {
     if ((rc = h->wt.f32("spk.w", static_cast<long long>(d) * cfg->spk_embed_dim, &h->spk_w))) return fail(rc);
     if ((rc = h->wt.f32("spk.b", d, &h->spk_b))) return fail(rc);
+  }
+  if (text_only) {
+    *out = h;
+    return 0;
   }
   if ((rc = load_conv(h->wt, "feat_out", 1, cfg->odim, d, true, true, cfg->odim, &h->feat_out))) return fail(rc);
   h->postnet.resize(cfg->postnet_layers);
@@ -377,6 +327,12 @@ extern "C" int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor*
   }
   *out = h;
   return 0;
+}
+}  // namespace jb
+
+extern "C" int jatts_fs2_create(const jatts_fs2_config* cfg, const jatts_tensor* weights, int32_t n_weights,
+                                jatts_fs2** out) {
+  return fs2_create_impl(cfg, weights, n_weights, false, out);
 }
 
 extern "C" void jatts_fs2_destroy(jatts_fs2* h) {
@@ -423,12 +379,16 @@ extern "C" int jatts_fs2_plan(jatts_fs2* h, const int64_t* d_tokens, const int32
     JB_PROPAGATE(add_speaker(d_spembs, c.spk_embed_dim, h->spk_w, h->spk_b, d, L, h->hs, s));
     JB_PROPAGATE(split_rows(h->hs, d, L, h->h_hi, h->h_lo, d, s));
   }
-  JB_PROPAGATE(predictor(h, h->pitch, L, h->s_pitch, s));
-  JB_PROPAGATE(predictor(h, h->energy, L, h->s_energy, s));
+  if (!h->text_only) {
+    JB_PROPAGATE(predictor(h, h->pitch, L, h->s_pitch, s));
+    JB_PROPAGATE(predictor(h, h->energy, L, h->s_energy, s));
+  }
   JB_PROPAGATE(predictor(h, h->dur, L, h->s_dur, s));
   JB_PROPAGATE(durations_and_scan(h->s_dur, alpha, L, h->d_text_off, h->o_dur, h->cum, h->d_nframes, s));
-  JB_PROPAGATE(gather_scalar(h->s_pitch, L, h->d_text_off, h->o_pitch, s));
-  JB_PROPAGATE(gather_scalar(h->s_energy, L, h->d_text_off, h->o_energy, s));
+  if (!h->text_only) {
+    JB_PROPAGATE(gather_scalar(h->s_pitch, L, h->d_text_off, h->o_pitch, s));
+    JB_PROPAGATE(gather_scalar(h->s_energy, L, h->d_text_off, h->o_energy, s));
+  }
   JB_CUDA_OK(cudaMemcpyAsync(h->h_nframes, h->d_nframes, sizeof(int) * n_utt, cudaMemcpyDeviceToHost, s));
   JB_CUDA_OK(cudaStreamSynchronize(s));
   for (int i = 0; i < n_utt; ++i) {
@@ -444,6 +404,7 @@ extern "C" int jatts_fs2_plan(jatts_fs2* h, const int64_t* d_tokens, const int32
 extern "C" int jatts_fs2_run(jatts_fs2* h, float* d_mel, int64_t* d_durations, float* d_pitch, float* d_energy,
                              int32_t* d_lr_index, void* stream) {
   JB_REQUIRE(h && d_mel && d_durations && d_pitch && d_energy, JATTS_E_INVALID, "fs2_run: null argument");
+  JB_REQUIRE(!h->text_only, JATTS_E_STATE, "fs2_run on a text-only engine");
   JB_REQUIRE(h->planned, JATTS_E_STATE, "fs2_run called without a successful fs2_plan");
   JB_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -480,7 +441,7 @@ extern "C" int jatts_fs2_run(jatts_fs2* h, float* d_mel, int64_t* d_durations, f
   }
   // The text-level layout tables (phase 0) stay valid; the text mask/seg arrays are about to be
   // overwritten by the frame layout, so the regulator only uses seg_start/seg_len of the text layout.
-  RowLayout Lt = device_layout(h, h->text, 0);
+  RowLayout Lt = fs2_device_layout(h, h->text, 0);
   JB_PROPAGATE(upload_layout(h, h->frame, 1, s, &h->Lf, &h->d_frame_off));
   const RowLayout& L = h->Lf;
   JB_PROPAGATE(zero_operand_gaps(h, L, s));
@@ -493,7 +454,7 @@ extern "C" int jatts_fs2_run(jatts_fs2* h, float* d_mel, int64_t* d_durations, f
   const int od_pad = round_up(c.odim, 64), pn = round_up(c.postnet_chans, 64);
   ConvGemmEpilogue ef{};
   ef.out_f32 = h->before; ef.out_f32_ld = c.odim; ef.out_hi = h->b_hi; ef.out_lo = h->b_lo; ef.out_bf_ld = od_pad;
-  JB_PROPAGATE(run_conv(h->feat_out, h->h_hi, h->h_lo, d, L, ef, s));
+  JB_PROPAGATE(split_conv(h->feat_out, h->h_hi, h->h_lo, d, L, ef, s));
   // postnet (pre_postnets.py:108-185), BatchNorm folded into the conv weights/bias on the host
   const bf16 *in_hi = h->b_hi, *in_lo = h->b_lo;
   int in_ld = od_pad;
@@ -507,7 +468,7 @@ extern "C" int jatts_fs2_run(jatts_fs2* h, float* d_mel, int64_t* d_durations, f
     } else {
       e.res_f32 = h->before; e.res_ld = c.odim; e.out_f32 = h->after; e.out_f32_ld = c.odim;  // fastspeech2.py:649
     }
-    JB_PROPAGATE(run_conv(h->postnet[i], in_hi, in_lo, in_ld, L, e, s));
+    JB_PROPAGATE(split_conv(h->postnet[i], in_hi, in_lo, in_ld, L, e, s));
     in_hi = o_hi; in_lo = o_lo; in_ld = pn;
   }
   JB_PROPAGATE(unpack_rows(h->after, c.odim, c.odim, L, h->d_frame_off, d_mel, s));

@@ -36,6 +36,11 @@ int relpos_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, const
                      int pos_rows, int n_head, int d_model, RowLayout L, int max_len, float* scratch,
                      size_t scratch_bytes, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s);
 
+// plain scaled-dot-product self attention on the same kernel: x = [q | k | v] ([x_rows, 3*D] operand pairs, no bias
+// folding), softmax(q k^T / sqrt(d_k)) v per utterance and head (the Matcha decoder's transformer blocks)
+int plain_attention(const bf16* x_hi, const bf16* x_lo, long long x_rows, int n_head, int d_model, RowLayout L, int max_len,
+                    float* scratch, size_t scratch_bytes, bf16* out_hi, bf16* out_lo, int out_ld, cudaStream_t s);
+
 // depthwise Conv1d (BatchNorm folded into wT/bias on the host) -> Swish (convolution.py:74-75)
 // g: [rows, C] fp32 (GLU output), wT: [k][C], out: hi/lo bf16
 // max_len >= every utterance length (sizes the strip grid)
@@ -72,5 +77,17 @@ int pack_mel_affine(const float* mel, int c, const float* a, const float* b, Row
 // wave: fp32, utterance-contiguous [sum T*rate] and / or pcm: int16 = lrintf(wave * 32767) (either may be null)
 int output_conv_tanh(const bf16* x, int ld, int c, const float* w /*[k][c]*/, float bias, int k, RowLayout L,
                      int rate, const int* frame_off, float* wave, short* pcm, cudaStream_t s);
+
+// ---- Matcha-TTS flow-matching decoder (kernels_matcha.cu) ----
+// y = Mish(GroupNorm_groups(x)) [+ add[c]] per utterance (decoder.py:65-96 Block1D / ResnetBlock1D); stats: scratch of
+// nseg * groups float2; outputs (each optional): y fp32, hi/lo operand pair whose gap rows are written as zeros
+int groupnorm_mish_rows(const float* x, int c, int groups, const float* gamma, const float* beta, float eps, const float* add,
+                        RowLayout L, float2* stats, float* y, bf16* hi, bf16* lo, int bf_ld, cudaStream_t s);
+// SnakeBeta after its Linear (transformer.py:28-102): x + sin(x * a)^2 * ib, a = exp(alpha), ib = 1 / (exp(beta) + 1e-9)
+int snake_beta_rows(const float* x, int c, const float* a, const float* ib, RowLayout L, bf16* hi, bf16* lo, int bf_ld,
+                    cudaStream_t s);
+// utterance-contiguous fp32 [sum T, c] * scale -> packed fp32 rows + operand pair (gap rows of the pair zeroed)
+int pack_rows_split(const float* in, int c, float scale, RowLayout L, const int* off, float* y, int y_ld, bf16* hi, bf16* lo,
+                    int bf_ld, cudaStream_t s);
 
 }  // namespace jb

@@ -208,6 +208,151 @@ def make_fs2_state_dict(cfg: dict, seed: int = 0, stress: bool = True,
     return sd
 
 
+# --------------------------------------------------------------------------------------------
+# Matcha-TTS (egs/jsut/tts1/conf/matcha_tts.v1.prior.steplr.large.yaml:22-61; BASELINE config 5)
+# --------------------------------------------------------------------------------------------
+JSUT_MATCHA = dict(
+    idim=45, odim=80, adim=384, aheads=2, elayers=4, eunits=1536,
+    positionwise_layer_type="conv1d", positionwise_conv_kernel_size=3,
+    duration_predictor_layers=2, duration_predictor_chans=256, duration_predictor_kernel_size=3, use_masking=True,
+    encoder_normalize_before=True, reduction_factor=1, encoder_type="conformer",
+    conformer_pos_enc_layer_type="rel_pos", conformer_self_attn_layer_type="rel_selfattn",
+    conformer_activation_type="swish", use_macaron_style_in_conformer=True, use_cnn_in_conformer=True,
+    conformer_enc_kernel_size=7, conformer_dec_kernel_size=31, init_type="xavier_uniform",
+    transformer_enc_dropout_rate=0.2, transformer_enc_positional_dropout_rate=0.2, transformer_enc_attn_dropout_rate=0.2,
+    decoder_channels=[512, 512], decoder_dropout=0.05, decoder_attention_head_dim=256, decoder_n_blocks=1,
+    decoder_num_mid_blocks=2, decoder_num_heads=2, decoder_act_fn="snakebeta",
+)
+MATCHA_ODE_STEPS, MATCHA_TEMPERATURE = 10, 0.667          # ode_steps / temperature of the same yaml (:78-79)
+# the same structure at a size the CPU oracle finishes in seconds (every width a shape the CUDA path implements)
+SMALL_MATCHA = dict(
+    JSUT_MATCHA, idim=30, odim=16, adim=128, eunits=256, elayers=2, duration_predictor_chans=64,
+    decoder_channels=[64, 64], decoder_attention_head_dim=64, decoder_num_heads=2,
+)
+
+
+def matcha_state_shapes(cfg: dict) -> "OrderedDict[str, tuple]":
+    """state_dict layout of jatts.models.MatchaTTS at this configuration, in the reference's registration order
+    (matchatts.py:196-313, jatts/modules/matchatts/decoder.py:243-392)"""
+    text = dict(cfg, dlayers=0, dunits=cfg["eunits"], postnet_layers=0, postnet_chans=0, postnet_filts=1,
+                pitch_predictor_layers=0, pitch_predictor_chans=0, pitch_predictor_kernel_size=1, pitch_embed_kernel_size=1,
+                energy_predictor_layers=0, energy_predictor_chans=0, energy_predictor_kernel_size=1, energy_embed_kernel_size=1)
+    fs2 = fs2_state_shapes(text)
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    D, od = cfg["adim"], cfg["odim"]
+    for k, v in fs2.items():
+        if k.startswith("encoder.") or k.startswith("projection."):
+            s[k] = v
+    s["encoder_proj.weight"] = (od, D)
+    s["encoder_proj.bias"] = (od,)
+    for k, v in fs2.items():
+        if k.startswith("duration_predictor."):
+            s[k] = v
+    e = "decoder.estimator."
+    chans = list(cfg["decoder_channels"])
+    in_ch, ted = 2 * od, chans[0] * 4
+    inner = cfg["decoder_num_heads"] * cfg["decoder_attention_head_dim"]
+    s[e + "time_mlp.linear_1.weight"] = (ted, in_ch)
+    s[e + "time_mlp.linear_1.bias"] = (ted,)
+    s[e + "time_mlp.linear_2.weight"] = (ted, ted)
+    s[e + "time_mlp.linear_2.bias"] = (ted,)
+
+    def resnet(p, ci, co):
+        s[p + "mlp.1.weight"] = (co, ted)
+        s[p + "mlp.1.bias"] = (co,)
+        for b, c_in in (("block1", ci), ("block2", co)):
+            s[p + b + ".block.0.weight"] = (co, c_in, 3)
+            s[p + b + ".block.0.bias"] = (co,)
+            s[p + b + ".block.1.weight"] = (co,)
+            s[p + b + ".block.1.bias"] = (co,)
+        s[p + "res_conv.weight"] = (co, ci, 1)
+        s[p + "res_conv.bias"] = (co,)
+
+    def transformer(p, c):
+        s[p + "norm1.weight"] = (c,)
+        s[p + "norm1.bias"] = (c,)
+        for n in ("q", "k", "v"):
+            s[p + f"attn1.to_{n}.weight"] = (inner, c)
+        s[p + "attn1.to_out.0.weight"] = (c, inner)
+        s[p + "attn1.to_out.0.bias"] = (c,)
+        s[p + "norm3.weight"] = (c,)
+        s[p + "norm3.bias"] = (c,)
+        s[p + "ff.net.0.alpha"] = (4 * c,)
+        s[p + "ff.net.0.beta"] = (4 * c,)
+        s[p + "ff.net.0.proj.weight"] = (4 * c, c)
+        s[p + "ff.net.0.proj.bias"] = (4 * c,)
+        s[p + "ff.net.2.weight"] = (c, 4 * c)
+        s[p + "ff.net.2.bias"] = (c,)
+
+    nb = cfg["decoder_n_blocks"]
+    co = in_ch
+    for i, c in enumerate(chans):
+        ci, co = co, c
+        resnet(f"{e}down_blocks.{i}.0.", ci, co)
+        for j in range(nb):
+            transformer(f"{e}down_blocks.{i}.1.{j}.", co)
+        q = f"{e}down_blocks.{i}.2." + ("" if i == len(chans) - 1 else "conv.")
+        s[q + "weight"] = (co, co, 3)
+        s[q + "bias"] = (co,)
+    for i in range(cfg["decoder_num_mid_blocks"]):
+        resnet(f"{e}mid_blocks.{i}.0.", chans[-1], chans[-1])
+        for j in range(nb):
+            transformer(f"{e}mid_blocks.{i}.1.{j}.", chans[-1])
+    up = chans[::-1] + [chans[0]]
+    for i in range(len(up) - 1):
+        ci, co = up[i], up[i + 1]
+        resnet(f"{e}up_blocks.{i}.0.", 2 * ci, co)
+        for j in range(nb):
+            transformer(f"{e}up_blocks.{i}.1.{j}.", co)
+        if i == len(up) - 2:
+            s[f"{e}up_blocks.{i}.2.weight"] = (co, co, 3)
+            s[f"{e}up_blocks.{i}.2.bias"] = (co,)
+        else:
+            s[f"{e}up_blocks.{i}.2.conv.weight"] = (co, co, 4)   # ConvTranspose1d (C_in, C_out, k)
+            s[f"{e}up_blocks.{i}.2.conv.bias"] = (co,)
+    s[e + "final_block.block.0.weight"] = (up[-1], up[-1], 3)
+    s[e + "final_block.block.0.bias"] = (up[-1],)
+    s[e + "final_block.block.1.weight"] = (up[-1],)
+    s[e + "final_block.block.1.bias"] = (up[-1],)
+    s[e + "final_proj.weight"] = (od, up[-1], 1)
+    s[e + "final_proj.bias"] = (od,)
+    return s
+
+
+def make_matcha_state_dict(cfg: dict, seed: int = 0, duration_recipe: str = "A") -> "OrderedDict[str, torch.Tensor]":
+    """Seeded Matcha-TTS weights: the text side exactly as ``make_fs2_state_dict`` (stress mode), the decoder with
+    xavier weights, perturbed biases / norm affines and SnakeBeta log-scale parameters away from their zero init."""
+    text = dict(cfg, dlayers=0, dunits=cfg["eunits"], postnet_layers=0, postnet_chans=0, postnet_filts=1,
+                pitch_predictor_layers=0, pitch_predictor_chans=0, pitch_predictor_kernel_size=1, pitch_embed_kernel_size=1,
+                energy_predictor_layers=0, energy_predictor_chans=0, energy_predictor_kernel_size=1, energy_embed_kernel_size=1)
+    fs2 = make_fs2_state_dict(text, seed, True, duration_recipe)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shape in matcha_state_shapes(cfg).items():
+        if name in fs2:
+            sd[name] = fs2[name]
+            continue
+        g = _gen("matcha." + name, seed)
+        leaf = name.rsplit(".", 1)[-1]
+        is_norm = ".norm1." in name or ".norm3." in name or ".block.1." in name
+        if leaf in ("alpha", "beta"):
+            t = 0.3 * (torch.rand(shape, generator=g) * 2 - 1)
+        elif is_norm and leaf == "weight":
+            t = 1.0 + 0.1 * (torch.rand(shape, generator=g) * 2 - 1)
+        elif len(shape) >= 2:
+            t = _xavier(shape, g)
+        elif leaf == "bias":
+            t = 0.05 * (torch.rand(shape, generator=g) * 2 - 1)
+        else:
+            raise AssertionError(name)
+        sd[name] = t.float()
+    return sd
+
+
+def make_noise(frames: int, odim: int, seed: int) -> torch.Tensor:
+    """standard-normal z (frames, odim) for the flow-matching decoder"""
+    return torch.randn(frames, odim, generator=torch.Generator().manual_seed(7000 + seed))
+
+
 def make_phonemes(t_text: int, seed: int, idim: int = 45) -> torch.Tensor:
     """ids 0 (<blank>/pad) and 1 (<unk>) avoided, idim-1 (<sos/eos>) unused."""
     g = torch.Generator().manual_seed(seed)

@@ -87,7 +87,7 @@ def run_case(lens, n_head, d, seed, pos_rows=None, scale=1.0):
 @pytest.mark.parametrize("lens,n_head,d", [
     ([1], 2, 384), ([2, 3], 2, 384), ([50, 49, 7], 2, 384), ([63, 64, 65], 2, 384),
     ([126, 127, 128, 129], 2, 384), ([300, 293, 311], 2, 384), ([255, 256, 257], 1, 128),
-    ([200, 31], 4, 256), ([130, 5], 3, 192),
+    ([200, 31], 4, 256), ([130, 5], 3, 192), ([150, 260, 9], 2, 512),
 ])
 def test_attention_matches_fp64_reference(lens, n_head, d):
     err = run_case(lens, n_head, d, seed=sum(lens) + d)
@@ -115,6 +115,58 @@ def test_many_utterances_persistent_tiles():
 def test_large_scores_softmax_is_stable():
     err = run_case([140, 33], 2, 384, seed=5, scale=4.0)     # |scores| of several hundred before the max subtraction
     assert err < 2e-4, err
+
+
+def run_plain_case(lens, n_head, d, seed, scale=1.0):
+    """plain scaled-dot-product attention (the Matcha decoder's transformer blocks: diffusers ``Attention`` as restated
+    in oracle/matcha.py::attention between to_q/k/v and to_out): x = [q | k | v], no positional table"""
+    g = torch.Generator().manual_seed(seed)
+    seg_start, rows = [], 0
+    for t in lens:
+        seg_start.append(rows)
+        rows += t + GAP
+    x_rows = rows + 64
+    x = torch.randn(x_rows, 3 * d, generator=g) * 7.0
+    for s0, t in zip(seg_start, lens):
+        x[s0:s0 + t] = torch.randn(t, 3 * d, generator=g) * scale
+    x_hi, x_lo = _pack.split16(x)
+    dev = "cuda"
+    xh, xl = x_hi.contiguous().to(dev), x_lo.contiguous().to(dev)
+    out_hi = torch.full((x_rows, d), float("nan"), dtype=torch.float16, device=dev)
+    out_lo = torch.full((x_rows, d), float("nan"), dtype=torch.float16, device=dev)
+    ss = torch.tensor(seg_start, dtype=torch.int32, device=dev)
+    sl = torch.tensor(lens, dtype=torch.int32, device=dev)
+    a = _lib.RelposAttentionArgs(
+        d_x_hi=xh.data_ptr(), d_x_lo=xl.data_ptr(), x_rows=x_rows, d_pos_hi=None, d_pos_lo=None, pos_rows=0,
+        n_head=n_head, d_model=d, d_seg_start=ss.data_ptr(), d_seg_len=sl.data_ptr(), nseg=len(lens), max_len=max(lens),
+        d_out_hi=out_hi.data_ptr(), d_out_lo=out_lo.data_ptr(), out_ld=d)
+    _lib.check(_lib.lib.jatts_op_relpos_attention(C.byref(a), torch.cuda.current_stream().cuda_stream), "op_relpos_attention")
+    torch.cuda.synchronize()
+    got = out_hi.double().cpu() + out_lo.double().cpu() / _pack.SPLIT_SCALE
+    xr = x_hi.double() + x_lo.double() / _pack.SPLIT_SCALE
+    worst, dk = 0.0, d // n_head
+    for s0, t in zip(seg_start, lens):
+        blk = xr[s0:s0 + t]
+        hv = lambda z: z.reshape(t, n_head, dk).transpose(0, 1)
+        attn = torch.softmax(torch.matmul(hv(blk[:, :d]), hv(blk[:, d:2 * d]).transpose(-2, -1)) / math.sqrt(dk), dim=-1)
+        ref = torch.matmul(attn, hv(blk[:, 2 * d:])).transpose(0, 1).reshape(t, d)
+        err = float((got[s0:s0 + t] - ref).abs().max())
+        assert math.isfinite(err), "non-finite output inside an utterance"
+        worst = max(worst, err / max(1.0, float(ref.abs().max())))
+    inside = torch.zeros(x_rows, dtype=torch.bool)
+    for s0, t in zip(seg_start, lens):
+        inside[s0:s0 + t] = True
+    assert bool(torch.isnan(out_hi.cpu()[~inside].float()).all()), "a gap row was written"
+    return worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lens,n_head,d", [
+    ([2], 2, 512), ([150, 151, 64], 2, 512), ([300, 2, 129, 600], 2, 512), ([127, 128, 254], 2, 128), ([90, 260], 1, 192),
+])
+def test_plain_attention_matches_fp64_reference(lens, n_head, d):
+    err = run_plain_case(lens, n_head, d, seed=sum(lens) + d + 1)
+    assert err < 2e-5, err
 
 
 @pytest.mark.gpu
