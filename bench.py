@@ -8,6 +8,7 @@ public API (``FastSpeech2.inference_batch`` -> ``Vocoder.decode_batch``).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference ...                     # the reference's CPU arithmetic (oracle port)
+  python bench.py --workload matcha64 ...                  # BASELINE config 5: Matcha-TTS (10 Euler steps) + HiFi-GAN, weak scaling
   python bench.py --workload voc10k ...                    # BASELINE config 4: 10 k mel clips, vocoder only, STRONG scaling
 
 Under torchrun (N > 1) every rank owns one GPU and its own 64-utterance batch (weak scaling, no
@@ -165,6 +166,58 @@ def time_cpu(n_utt: int, reps: int, warm: int, seed0: int = 0, keep=None):
     return audio_s, times
 
 
+def matcha_decoder_flops(cfg, frames) -> float:
+    """algorithmic FLOP (2 per multiply-add, each product counted ONCE although the split GEMM issues three MMAs) of one
+    Euler step of the flow-matching U-Net (jatts/modules/matchatts/decoder.py:413-487) for utterances of ``frames`` frames"""
+    c, od = cfg["decoder_channels"][0], cfg["odim"]
+    inner = cfg["decoder_num_heads"] * cfg["decoder_attention_head_dim"]
+    nb, nm = cfg["decoder_n_blocks"], cfg["decoder_num_mid_blocks"]
+    total = 0.0
+    for t in frames:
+        t -= t % 2
+        th = t // 2
+        res = lambda rows, cin: 2.0 * rows * (3 * cin * c + 3 * c * c + cin * c)
+        tr = lambda rows: nb * (2.0 * rows * (c * 3 * inner + inner * c + c * 4 * c + 4 * c * c) + 4.0 * rows * rows * inner)
+        total += res(t, 2 * od) + tr(t) + 2.0 * th * 3 * c * c                       # down 0 + stride-2 conv
+        total += res(th, c) + tr(th) + 2.0 * th * 3 * c * c                          # down 1 + conv
+        total += nm * (res(th, c) + tr(th))                                          # mid
+        total += res(th, 2 * c) + tr(th) + 2.0 * th * 4 * c * c                      # up 0 + ConvTranspose1d(4, 2, 1)
+        total += res(t, 2 * c) + tr(t) + 2.0 * t * 3 * c * c                         # up 1 + conv
+        total += 2.0 * t * 3 * c * c + 2.0 * t * c * od                              # final block + projection
+    return total
+
+
+def time_cpu_matcha(n_utt: int, reps: int, warm: int, keep=None):
+    """config 5 on the host cores: oracle port of MatchaTTS.inference + the restated vocoder, per-utterance loop"""
+    from oracle import hifigan as ohg
+    from oracle import matcha as om
+    from oracle import recipes
+
+    cfg, cfg_hg = recipes.JSUT_MATCHA, recipes.HIFIGAN_V1_HOP300
+    sd = recipes.make_matcha_state_dict(cfg, seed=0, duration_recipe="A")
+    sd_hg = recipes.make_hifigan_state_dict(cfg_hg, seed=0)
+    texts = [recipes.make_phonemes(T_TEXT, i, cfg["idim"]) for i in range(n_utt)]
+
+    def one(i, x):
+        z = recipes.make_noise(1024, cfg["odim"], i).t()
+        out = om.matcha_inference(sd, cfg, x, z, recipes.MATCHA_ODE_STEPS, recipes.MATCHA_TEMPERATURE)
+        return out, ohg.hifigan_forward(sd_hg, cfg_hg, out["feat_gen"]).reshape(-1)
+
+    for _ in range(warm):
+        one(0, texts[0])
+    times, frames = [], 0
+    for r in range(reps):
+        t0 = time.perf_counter()
+        frames = 0
+        for i, x in enumerate(texts):
+            out, wav = one(i, x)
+            frames += out["feat_gen"].shape[0]
+            if keep is not None and r == 0:
+                keep.append((out, wav))
+        times.append(time.perf_counter() - t0)
+    return frames * recipes.HOP_SIZE / recipes.SAMPLING_RATE, times
+
+
 def time_cpu_vocoder(n_clips: int, reps: int, warm: int):
     """config 4 on the host cores: the restated generator on the first clips of the 10 k list"""
     from oracle import hifigan as ohg
@@ -196,6 +249,12 @@ def run_reference(args, rank: int, world: int):
         sample = (f"{n} of the 10000 clips per step, per-clip loop as vocoder.py:56-67; restated HiFi-GAN V1 generator "
                   f"(oracle port, fp32 torch CPU)")
         extra = {"sample_clips_per_step": n}
+    elif args.workload == "matcha64":
+        n = 1
+        audio_s, times = time_cpu_matcha(n, reps=args.steps, warm=min(args.warmup, 1))
+        sample = (f"{n} of the {BATCH} utterances per step, per-utterance loop as tts_decode.py; oracle port of MatchaTTS.inference "
+                  f"(10 Euler steps) + restated HiFi-GAN V1 (fp32 torch CPU)")
+        extra = {"sample_utterances_per_step": n}
     else:
         n = 2  # bounded sample of the 64-utterance step
         audio_s, times = time_cpu(n, reps=args.steps, warm=min(args.warmup, 2))
@@ -315,6 +374,11 @@ def workload_config(workload: str, world: int, extra: dict) -> dict:
                            "frames, N(0,1), seed = clip index), utterance-sharded over the GPUs (BASELINE config 4), seeded "
                            "random-init weights", "clips": 10000, "clips_per_launch": VOC_BATCH,
                "parallelism": f"clips sharded by greedy LPT over {world} rank(s), no collective on the data path"}
+    elif workload == "matcha64":
+        cfg = {"workload": "Matcha-TTS (JSUT tts1 matcha_tts.v1.prior.steplr.large: 512-wide U-Net, 2 heads x 256, predicted durations) "
+                           "with 10 Euler steps at temperature 0.667 + HiFi-GAN V1 hop 300, batch 64 x 50 phonemes (~300 frames each) "
+                           "per GPU (BASELINE config 5), seeded random-init weights (duration recipe A)",
+               "batch_per_gpu": BATCH, "t_text": T_TEXT, "ode_steps": 10, "parallelism": f"utterance-sharded replicas x{world}"}
     else:
         cfg = {"workload": "FastSpeech2 (JSUT tts1) + HiFi-GAN V1 hop 300, batch 64 x 50 phonemes (~300 frames each) per GPU, "
                            "seeded random-init weights (duration recipe A)",
@@ -492,6 +556,138 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
 
 
+def run_matcha64(args, rank: int, world: int, local_rank: int):
+    """BASELINE config 5: Matcha-TTS text2mel (10 Euler steps) + HiFi-GAN, batch 64 per GPU, weak scaling."""
+    import jatts_b200
+    from jatts_b200 import _lib
+    from oracle import recipes
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg, cfg_hg = recipes.JSUT_MATCHA, recipes.HIFIGAN_V1_HOP300
+    steps_ode, temp = recipes.MATCHA_ODE_STEPS, recipes.MATCHA_TEMPERATURE
+    model = jatts_b200.MatchaTTS(**cfg)
+    model.load_state_dict(recipes.make_matcha_state_dict(cfg, seed=0, duration_recipe="A"))
+    model = model.eval().to(dev)
+    stats = {"mean": torch.zeros(80), "scale": torch.ones(80)}
+    voc = jatts_b200.Vocoder(recipes.make_hifigan_state_dict(cfg_hg, seed=0),
+                             {"generator_type": "HiFiGANGenerator", "generator_params": dict(cfg_hg),
+                              "sampling_rate": recipes.SAMPLING_RATE}, stats, dev, trg_stats=stats)
+    # rank 0's first utterances are the ones the CPU arm synthesises (seeds 0, 1, ...): the parity check below
+    texts_cpu = [recipes.make_phonemes(T_TEXT, 1000 * rank + i, cfg["idim"]) for i in range(BATCH)]
+    tok_host = torch.cat(texts_cpu).pin_memory()
+    texts_dev = [t.to(dev) for t in texts_cpu]
+    noise_dev = {}
+
+    def fixed_noise(frames):   # the seeded z of oracle/recipes.py, resident on the device after the first call
+        key = tuple(frames)
+        if key not in noise_dev:
+            noise_dev[key] = [recipes.make_noise(1024, cfg["odim"], i)[:f].to(dev) for i, f in enumerate(frames)]
+        return noise_dev[key]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    timed = Timer(dev, world, flush)
+
+    def step_device():
+        outs = model.inference_batch(texts_dev, n_timesteps=steps_ode, temperature=temp, noise=fixed_noise)
+        waves = voc.decode_batch([o["feat_gen"] for o in outs])
+        return outs, waves
+
+    wave_host = None
+
+    def step_e2e():   # the call a user makes: host tokens in, noise drawn on the device, host waveform out
+        nonlocal wave_host
+        tok = tok_host.to(dev, non_blocking=True)
+        outs = model.inference_batch(list(tok.split(T_TEXT)), n_timesteps=steps_ode, temperature=temp)
+        flat = torch.cat(voc.decode_batch([o["feat_gen"] for o in outs]))
+        if wave_host is None or wave_host.numel() != flat.numel():
+            wave_host = torch.empty(flat.numel(), dtype=torch.float32).pin_memory()
+        wave_host.copy_(flat, non_blocking=True)
+        return outs, flat
+
+    for _ in range(max(args.warmup, 3)):
+        outs, waves = step_device()
+    torch.cuda.synchronize(dev)
+    frames_l = [int(o["feat_gen"].shape[0]) for o in outs]
+    frames = sum(frames_l)
+    audio_s = frames * recipes.HOP_SIZE / recipes.SAMPLING_RATE
+    sampler = start_sampler(rank, local_rank, dev, step_device)
+    l0 = _lib.launch_count()
+    s0 = sampler.mark()
+    ms_dev = timed(step_device, args.steps)
+    launches = (_lib.launch_count() - l0) // args.steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop(s0, sampler.mark()) if rank == 0 else None
+    # per-class device time of one text2mel call and one vocoder call (per-launch CUDA events)
+    _lib.profile_begin()
+    model.inference_batch(texts_dev, n_timesteps=steps_ode, temperature=temp, noise=fixed_noise)
+    t2m = _lib.profile_end_classes()
+    mels = [o["feat_gen"] for o in outs]
+    ms_conv, n_conv, _, _ = hifigan_roofline(_lib, lambda: voc.decode_batch(mels), frames, cfg_hg, seconds=0.5)
+    (ms_dev, ms_e2e), total_audio = reduce_times(world, dev, [ms_dev, ms_e2e], audio_s)
+    if rank != 0:
+        return
+    pk = peaks()
+    dec_flop = matcha_decoder_flops(cfg, frames_l) * steps_ode
+    enc_flop = BATCH * fs2_flops(dict(recipes.JSUT_FS2, dlayers=0, pitch_predictor_chans=0, energy_predictor_chans=0), T_TEXT, 0)
+    gemm_ms = t2m["split_gemm"][0]
+    achieved = (dec_flop + enc_flop) / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    cpu_cores = os.cpu_count() or 1
+    torch.set_num_threads(cpu_cores)
+    kept = []
+    cpu_audio, cpu_times = time_cpu_matcha(2, reps=3, warm=1, keep=kept)
+    cpu_value = cpu_audio * len(cpu_times) / sum(cpu_times)
+    from oracle import hifigan as ohg
+    parity = {"rows": 2, "durations_equal": True, "mel_max_abs": 0.0, "wave_ac_snr_db": 1e9}
+    for i in range(2):   # rows 0 and 1 of the TIMED batch against the oracle (same tokens, same noise)
+        ref, wref = kept[i]
+        parity["durations_equal"] &= bool(torch.equal(ref["duration"], outs[i]["duration"].cpu()))
+        if ref["feat_gen"].shape == outs[i]["feat_gen"].shape:
+            parity["mel_max_abs"] = max(parity["mel_max_abs"], float((ref["feat_gen"] - outs[i]["feat_gen"].cpu()).abs().max()))
+            parity["wave_ac_snr_db"] = min(parity["wave_ac_snr_db"], ohg.ac_snr_db(wref, waves[i].cpu().reshape(-1)))
+        else:
+            parity["durations_equal"] = False
+    parity_ok = parity["durations_equal"] and parity["mel_max_abs"] < 1e-3 and parity["wave_ac_snr_db"] >= 35.0
+    line = {
+        "metric": METRIC, "value": total_audio * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split / bf16", "data": "synthetic",
+        "config": workload_config("matcha64", world, {"mel_frames_per_gpu": frames, "audio_seconds_per_step_per_gpu": audio_s,
+                   "sampling_rate": recipes.SAMPLING_RATE, "hop_size": recipes.HOP_SIZE,
+                   "l2": "256 MB buffer written between timed steps; per-step activation working set >> 126 MB L2",
+                   "noise": "device-timed steps use the seeded z of oracle/recipes.py::make_noise resident on the device; the e2e "
+                            "steps draw z with torch.randn on the device inside the call, as the reference does",
+                   "precision": "Matcha text2mel: fp16 hi+lo split GEMMs and attention (3 MMA) / fp32; HiFi-GAN: bf16 operands / fp32 accumulate"}),
+        "e2e": {"value": total_audio * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(tok_host.numel() * 8), "d2h_bytes_per_step": int(frames * recipes.HOP_SIZE * 4),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "parity_checked": bool(parity_ok), "parity": parity,
+        "roofline": {"bound": "tensor",
+                     "kernel": "gemm_split_tma_kernel<*>: every Conv1d / Linear / ConvTranspose1d of the Matcha encoder and of the 10 "
+                               "evaluations of the flow-matching U-Net (fp16 hi+lo split operands: 3 tcgen05 MMAs per algorithmic product)",
+                     "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["sustained"] if achieved else None,
+                     "frac_of_issued_mma": 3.0 * achieved / pk["sustained"] if achieved else None,
+                     "peak_source": pk["source"] + ": bf16_tflops_sustained",
+                     "traffic": None, "launches_per_step": int(t2m["split_gemm"][1]), "kernel_ms_per_step": gemm_ms,
+                     "algorithmic_flop_per_step": dec_flop + enc_flop,
+                     "note": "achieved counts each product once; the kernel issues 3 MMAs per product (frac_of_issued_mma)",
+                     "matcha_attention": {"launches_per_step": int(t2m["attention"][1]), "kernel_ms_per_step": t2m["attention"][0]},
+                     "matcha_norm_act": {"launches_per_step": int(t2m["layernorm"][1]), "kernel_ms_per_step": t2m["layernorm"][0],
+                                         "what": "LayerNorm, GroupNorm statistics + Mish, SnakeBeta"},
+                     "hifigan_conv": {"launches_per_step": n_conv, "kernel_ms_per_step": ms_conv}},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "host_cpus": cpu_cores,
+                         "sample": "2 of the 64 utterances (50 phonemes each) x 3 repetitions after 1 warm-up, per-utterance loop as "
+                                   "tts_decode.py; oracle port of MatchaTTS.inference (10 Euler steps) + restated HiFi-GAN V1, fp32 torch "
+                                   "CPU, all host cores"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_voc10k(args, rank: int, world: int, local_rank: int):
     """BASELINE config 4: 10 k clips, STRONG scaling -- the clip list is fixed and sharded over the ranks."""
     import jatts_b200
@@ -583,8 +779,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="tts64", choices=["tts64", "voc10k"],
-                    help="tts64 = BASELINE config 2 (the headline, weak scaling); voc10k = config 4 (strong scaling)")
+    ap.add_argument("--workload", default="tts64", choices=["tts64", "voc10k", "matcha64"],
+                    help="tts64 = BASELINE config 2 (the headline, weak scaling); voc10k = config 4 (strong scaling); "
+                         "matcha64 = config 5 (Matcha-TTS + HiFi-GAN, weak scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -601,6 +798,8 @@ def main():
     try:
         if args.workload == "voc10k":
             run_voc10k(args, rank, world, local_rank)
+        elif args.workload == "matcha64":
+            run_matcha64(args, rank, world, local_rank)
         else:
             run_b200(args, rank, world, local_rank)
     finally:

@@ -244,12 +244,15 @@ class WavWriter:
 # the decode loop
 # --------------------------------------------------------------------------------------------------------------
 def decode_items(model, vocoder, items: Sequence[dict], outdir: str, sampling_rate: int, device, max_utts: int = 64,
-                 max_tokens: int = 8192, spembs=None, rank: int = 0, world_size: int = 1, writer_threads: int = 4) -> dict:
+                 max_tokens: int = 8192, spembs=None, rank: int = 0, world_size: int = 1, writer_threads: int = 4,
+                 inference_kwargs: Optional[dict] = None) -> dict:
     """Synthesise this rank's share of ``items`` (dicts with ``sample_id`` and ``token_indices``) into
     ``outdir/wav/<sample_id>.wav``.  ``spembs``: a ``SpeakerEmbeddingCache`` (or a plain dict keyed by ``sample_id`` /
     ``ref_wav_path``) for multi-speaker models.  With ``world_size > 1`` every rank calls this with the same ``items``
     and decodes the utterances ``shard_utterances`` assigns to it (no communication; each file is written by exactly
-    one rank).  Returns counters (utterances, batches, frames, audio seconds, wall seconds) of this rank."""
+    one rank).  ``inference_kwargs``: extra keyword arguments of ``model.inference_batch`` (Matcha-TTS: ``n_timesteps`` and
+    ``temperature``, tts_decode.py:216-226).  Returns counters (utterances, batches, frames, audio seconds, wall seconds)
+    of this rank."""
     import torch
 
     from .shard import shard_utterances
@@ -284,7 +287,7 @@ def decode_items(model, vocoder, items: Sequence[dict], outdir: str, sampling_ra
                 raise ValueError("the model is speaker conditioned: pass speaker embeddings (--spkemb-npz)")
             sp = torch.stack([spembs(items[j]) for j in batch]).to(device)
         try:
-            outs = model.inference_batch(texts, spembs=sp)
+            outs = model.inference_batch(texts, spembs=sp, **(inference_kwargs or {}))
         finally:
             h2d.synchronize()
             tok_ring.release(tk)
@@ -373,8 +376,10 @@ def main(argv=None) -> int:
     with open(args.config) as f:
         config = yaml.load(f, Loader=yaml.Loader)
     config.update(vars(args))
-    if config["model_type"] != "FastSpeech2":
-        raise NotImplementedError(f"model_type {config['model_type']}: only FastSpeech2 has a B200 path")
+    classes = {"FastSpeech2": jatts_b200.FastSpeech2, "FastSpeech2B200": jatts_b200.FastSpeech2,
+               "MatchaTTS": jatts_b200.MatchaTTS, "MatchaTTSB200": jatts_b200.MatchaTTS}
+    if config["model_type"] not in classes:
+        raise NotImplementedError(f"model_type {config['model_type']}: only FastSpeech2 and MatchaTTS have a B200 path")
     if not torch.cuda.is_available():
         raise RuntimeError("jatts_b200.decode needs a CUDA device (there is no CPU fallback)")
     if not 0 <= args.rank < args.world_size:
@@ -384,7 +389,11 @@ def main(argv=None) -> int:
     torch.cuda.set_device(device)
     items = read_items(args.csv, args.token_column, TokenIDConverter(args.token_list))
     logging.info(f"Dataset size = {len(items)}.")
-    model = jatts_b200.FastSpeech2(**config["model_params"], max_len=args.max_len)
+    model = classes[config["model_type"]](**config["model_params"], max_len=args.max_len)
+    # tts_decode.py:216-226: Matcha-TTS takes its solver settings from the top level of the training config
+    inference_kwargs = {}
+    if isinstance(model, jatts_b200.MatchaTTS):
+        inference_kwargs = {"temperature": config["temperature"], "n_timesteps": config["ode_steps"]}
     model.load_state_dict(torch.load(args.checkpoint, map_location="cpu")["model"])
     model = model.eval().to(device)
     logging.info(f"Loaded model parameters from {args.checkpoint}.")
@@ -405,7 +414,7 @@ def main(argv=None) -> int:
         spembs = SpeakerEmbeddingCache(table=dict(np.load(args.spkemb_npz)))
     res = decode_items(model, vocoder, items, args.outdir, vocoder.config["sampling_rate"], device, args.max_utts,
                        args.max_tokens, spembs, rank=args.rank, world_size=args.world_size,
-                       writer_threads=args.writer_threads)
+                       writer_threads=args.writer_threads, inference_kwargs=inference_kwargs)
     logging.info("rank %d/%d decoded %d utterances in %d batches: %.1f s of audio in %.2f s (%.0f x real time, %.0f utterances/s)%s" % (
         args.rank, args.world_size, res["utterances"], res["batches"], res["audio_seconds"], res["wall_seconds"],
         res["audio_seconds_per_second"], res["utterances_per_second"],

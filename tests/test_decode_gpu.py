@@ -130,3 +130,45 @@ def test_utterance_longer_than_max_len_is_reported_not_fatal(tmp_path):
     res = decode.decode_items(model, voc, items, str(tmp_path), 24000, torch.device("cuda"), max_utts=8)
     assert res["skipped"] == ["u2"] and res["files"] == 3
     assert sorted(p.name for p in (tmp_path / "wav").iterdir()) == ["u0.wav", "u1.wav", "u3.wav"]
+
+
+@pytest.mark.gpu
+def test_matcha_through_the_stage4_front_end(tmp_path):
+    """BASELINE config 5 through the same front-end (tts_decode.py:216-226 passes ``temperature`` / ``n_timesteps``):
+    one wav per utterance, hop x (even-truncated duration sum) samples, and -- the noise being drawn from the seeded CUDA
+    generator exactly once per batch -- the samples the ORACLE predicts from that noise."""
+    from oracle import matcha as om
+
+    cfg, hcfg = recipes.SMALL_MATCHA, dict(recipes.HIFIGAN_TINY, in_channels=recipes.SMALL_MATCHA["odim"])
+    sd = recipes.make_matcha_state_dict(cfg, 2)
+    model = jatts_b200.MatchaTTS(**cfg)
+    model.load_state_dict(sd)
+    model = model.eval().to("cuda")
+    tstats, vstats = recipes.make_stats(3, cfg["odim"]), recipes.make_stats(4, cfg["odim"])
+    hsd = recipes.make_hifigan_state_dict(hcfg, 1)
+    voc = jatts_b200.Vocoder(hsd, {"generator_type": "HiFiGANGenerator", "generator_params": dict(hcfg), "sampling_rate": 24000},
+                             vstats, "cuda", trg_stats=tstats)
+    lens = [6, 14, 9]
+    items = [{"sample_id": f"m{i}", "token_indices": recipes.make_phonemes(n, 70 + i, cfg["idim"]).tolist()} for i, n in enumerate(lens)]
+    kw = {"n_timesteps": 4, "temperature": 0.667}
+    torch.manual_seed(1234)
+    res = decode.decode_items(model, voc, items, str(tmp_path), 24000, torch.device("cuda"), max_utts=8, inference_kwargs=kw)
+    assert res["files"] == 3 and not res["skipped"]
+    # the front-end sorts by length into ONE batch here: reproduce its noise draw (matchatts.py: torch.randn(sum T, odim))
+    order = sorted(range(len(lens)), key=lambda j: lens[j])
+    texts = [torch.tensor(items[j]["token_indices"]) for j in order]
+    frames = [int(om.matcha_inference(sd, cfg, x, torch.zeros(cfg["odim"], 4096), 1, 0.0)["feat_gen"].shape[0]) for x in texts]
+    torch.manual_seed(1234)
+    z = torch.randn(sum(frames), cfg["odim"], device="cuda").cpu()
+    hop = 6
+    o = 0
+    for x, j, f in zip(texts, order, frames):
+        ref = om.matcha_inference(sd, cfg, x, z[o:o + f].t(), kw["n_timesteps"], kw["temperature"])
+        o += f
+        yref = ohg.vocoder_decode(hsd, hcfg, ref["feat_gen"], vstats, tstats)
+        with wave.open(str(tmp_path / "wav" / f"m{j}.wav"), "rb") as w:
+            got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.float32) / 32767.0
+        tot = int(ref["duration"].sum())
+        assert got.shape[0] == yref.shape[0] == (tot - tot % 2) * hop
+        snr = ohg.ac_snr_db(yref, torch.from_numpy(got))
+        assert snr > 35.0, f"m{j}: AC-SNR {snr:.1f} dB vs the oracle"
