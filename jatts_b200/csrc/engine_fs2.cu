@@ -267,7 +267,7 @@ int fs2_create_impl(const jatts_fs2_config* cfg, const jatts_tensor* weights, in
   JB_REQUIRE(cfg->adim % 64 == 0 && cfg->adim <= 512, JATTS_E_UNSUPPORTED, "adim must be a multiple of 64, <= 512");
   JB_REQUIRE(cfg->adim % cfg->aheads == 0, JATTS_E_INVALID, "adim % aheads");
   JB_REQUIRE(relpos_attention_supported(cfg->aheads, cfg->adim), JATTS_E_UNSUPPORTED,
-             "adim / aheads must be 64, 128 or 192 (head size of the tcgen05 attention kernel)");
+             "adim / aheads must be 64, 128, 192 or 256 (head size of the tcgen05 attention kernel)");
   JB_REQUIRE(cfg->eunits % 64 == 0 && cfg->dunits % 64 == 0, JATTS_E_UNSUPPORTED, "ffn units must be a multiple of 64");
   JB_REQUIRE(cfg->dur_chans % 64 == 0 && cfg->pitch_chans % 64 == 0 && cfg->energy_chans % 64 == 0 &&
                  cfg->dur_chans <= 512 && cfg->pitch_chans <= 512 && cfg->energy_chans <= 512,

@@ -174,8 +174,8 @@ class FastSpeech2(torch.nn.Module):
         need(spks is None or spks <= 1, "speaker-id embeddings (spks)")
         need(spk_embed_dim is None or spk_embed_dim <= 0 or spk_embed_integration_type == "add",
              "spk_embed_integration_type != 'add'")
-        need(aheads > 0 and adim % aheads == 0 and adim // aheads in (64, 128, 192),
-             f"adim/aheads = {adim}/{aheads} (the tcgen05 attention kernel implements head sizes 64, 128 and 192; there is "
+        need(aheads > 0 and adim % aheads == 0 and adim // aheads in (64, 128, 192, 256),
+             f"adim/aheads = {adim}/{aheads} (the tcgen05 attention kernel implements head sizes 64, 128, 192 and 256; there is "
              "no other attention path)")
         need(0 < max_len <= _pack.PE_MAX_LEN, "max_len outside (0, 5000] (positional table is rebuilt above 5000)")
         # the packed layout separates utterances by _pack.GAP_ROWS zero rows: a "same"-padded convolution must be
