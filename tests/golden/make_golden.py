@@ -1,8 +1,8 @@
 """Generate the golden vectors under tests/golden/ by running the REAL reference code.
 
 Run in the build container (where /root/reference exists):  python tests/golden/make_golden.py
-It imports the unmodified ``jatts.models.fastspeech2.FastSpeech2`` (oracle/ref_loader.py), loads the
-seeded weights of oracle/recipes.py into it and stores what ``inference()`` returns.  The files travel
+It imports the unmodified ``jatts.models.fastspeech2.FastSpeech2`` (and ``jatts.models.matchatts.MatchaTTS``) through
+oracle/ref_loader.py, loads the seeded weights of oracle/recipes.py into it and stores what ``inference()`` returns.  The files travel
 to the GPU box, the reference does not.
 """
 import os
@@ -35,6 +35,56 @@ def case_inputs(name):
     return cfg, wseed, recipe, texts, spembs, alpha
 
 
+# Matcha-TTS: name: (config name, weight seed, [text lengths], text seed base, Euler steps, temperature, spk)
+MATCHA_CASES = {
+    "matcha_small": ("SMALL_MATCHA", 3, [9, 17, 4], 500, 10, 0.667, False),
+    "matcha_small_spk": ("SMALL_MATCHA", 4, [12, 6], 600, 4, 0.5, True),
+    "matcha_jsut": ("JSUT_MATCHA", 5, [14], 700, 10, 0.667, False),
+}
+
+
+def matcha_case_inputs(name):
+    cfg_name, wseed, lens, tseed, steps, temp, spk = MATCHA_CASES[name]
+    cfg = dict(getattr(recipes, cfg_name))
+    if spk:
+        cfg.update(spk_embed_dim=24, spk_embed_integration_type="add")
+    texts = [recipes.make_phonemes(t, tseed + i, cfg["idim"]) for i, t in enumerate(lens)]
+    spembs = recipes.make_spembs(len(lens), tseed, 24) if spk else None
+    return cfg, wseed, texts, spembs, steps, temp
+
+
+def main_matcha():
+    """The REAL reference MatchaTTS (matchatts.py, flow_matching.py, decoder.py, transformer.py imported in place; the one
+    missing third-party class, diffusers' Attention, is the stand-in of oracle/ref_loader.py) run through its own
+    ``inference()``.  The noise it draws inside CFM.inference (``randn_like`` of a permuted view, CPU generator) is
+    reproduced with the same call and stored next to the output, so that the GPU box can feed the same z."""
+    import logging
+
+    logging.disable(logging.WARNING)
+    cls = ref_loader.load_reference_matcha()
+    for name in MATCHA_CASES:
+        cfg, wseed, texts, spembs, steps, temp = matcha_case_inputs(name)
+        sd = recipes.make_matcha_state_dict(cfg, seed=wseed, duration_recipe="A")
+        model = cls(**cfg)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        out = {}
+        with torch.no_grad():
+            for i, x in enumerate(texts):
+                torch.manual_seed(9000 + i)
+                r = model.inference(x, spembs=None if spembs is None else spembs[i], n_timesteps=steps, temperature=temp)
+                t_out = r["feat_gen"].shape[0]
+                torch.manual_seed(9000 + i)
+                z = torch.randn_like(torch.empty(1, t_out, cfg["odim"]).permute(0, 2, 1))[0]      # (odim, T) as drawn
+                out[f"feat_gen_{i}"] = r["feat_gen"].numpy().astype(np.float32)
+                out[f"duration_{i}"] = r["duration"].numpy().astype(np.int64)
+                out[f"noise_{i}"] = z.t().contiguous().numpy().astype(np.float32)                 # (T, odim)
+                print(name, i, "T_text", x.shape[0], "frames", t_out, "dur min/max", int(r["duration"].min()),
+                      int(r["duration"].max()), "|mel| max", float(r["feat_gen"].abs().max()))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    logging.disable(logging.NOTSET)
+
+
 def main():
     torch.set_num_threads(8)
     for name in CASES:
@@ -55,4 +105,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "matcha":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "matcha":
+        main_matcha()

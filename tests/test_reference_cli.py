@@ -99,6 +99,7 @@ def _standins():
     models = types.ModuleType("jatts.models")       # the real package star-imports Matcha / E2-TTS (missing deps)
     models.__path__ = [os.path.join(REF, "jatts", "models")]
     models.FastSpeech2B200 = jatts_b200.FastSpeech2
+    models.MatchaTTS = jatts_b200.MatchaTTS          # keeps the name: tts_decode.py:216-226 keys its solver kwargs on it
     mods["jatts.models"] = models
     return mods
 
@@ -198,6 +199,82 @@ def test_reference_cli_runs_to_the_end_with_our_objects(tmp_path):
     for i, x in enumerate(texts):
         ref = ofs2.fs2_inference(sd, cfg, x)
         # the reference Vocoder wrapper does the affine itself (vocoder.py:57-61) before calling our generator
+        yref = ohg.vocoder_decode(hsd, hcfg, ref["feat_gen"], vstats, tstats)
+        with wave.open(str(tmp_path / "out" / "wav" / f"utt{i}.wav"), "rb") as w:
+            assert w.getframerate() == 24000 and w.getsampwidth() == 2
+            got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+        want = np.rint(yref.double().numpy() * 32767.0).astype("<i2")
+        assert got.shape == want.shape and np.abs(got.astype(np.int32) - want).max() <= 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the same for Matcha-TTS (BASELINE config 5): the CLI passes temperature / n_timesteps from the config (tts_decode.py:216-226)
+# ---------------------------------------------------------------------------------------------------------------
+def _write_matcha_files(tmp_path):
+    from h5_writer import write_h5
+    from oracle import recipes
+
+    cfg = recipes.SMALL_MATCHA
+    hcfg = dict(recipes.HIFIGAN_TINY, in_channels=cfg["odim"])
+    sd = recipes.make_matcha_state_dict(cfg, seed=0)
+    hsd = recipes.make_hifigan_state_dict(hcfg, seed=0)
+    tstats, vstats = recipes.make_stats(1, cfg["odim"]), recipes.make_stats(2, cfg["odim"])
+    vocab = ["<blank>", "<unk>"] + [f"p{i}" for i in range(2, cfg["idim"] - 1)] + ["<sos/eos>"]
+    (tmp_path / "tokens.txt").write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    rows, texts = ["sample_id,phonemes"], []
+    for i, n in enumerate([6, 8]):
+        ids = recipes.make_phonemes(n, 820 + i, cfg["idim"]).tolist()
+        texts.append(torch.tensor(ids, dtype=torch.long))
+        rows.append(f"utt{i}," + " ".join(vocab[t] for t in ids))
+    (tmp_path / "dev.csv").write_text("\n".join(rows) + "\n", encoding="utf-8")
+    write_h5(tmp_path / "stats.h5", {"mel_mean": tstats["mean"].numpy(), "mel_scale": tstats["scale"].numpy()})
+    write_h5(tmp_path / "voc_stats.h5", {"mean": vstats["mean"].numpy(), "scale": vstats["scale"].numpy()})
+    torch.save({"model": {"generator": hsd}}, tmp_path / "voc.pkl")
+    plain = {k: (list(map(list, v)) if k == "resblock_dilations" else list(v) if isinstance(v, tuple) else v) for k, v in hcfg.items()}
+    with open(tmp_path / "voc_config.yml", "w") as f:
+        yaml.safe_dump({"generator_type": "HiFiGANGenerator", "sampling_rate": 24000, "generator_params": plain}, f)
+    torch.save({"model": sd}, tmp_path / "checkpoint-1steps.pkl")
+    with open(tmp_path / "config.yml", "w") as f:
+        yaml.safe_dump({"model_type": "MatchaTTS", "model_params": dict(cfg), "out_feat_type": "mel", "feat_list": ["mel"],
+                        "sampling_rate": 24000, "temperature": 0.667, "ode_steps": 3,
+                        "vocoder": {"checkpoint": str(tmp_path / "voc.pkl"), "config": str(tmp_path / "voc_config.yml"),
+                                    "stats": str(tmp_path / "voc_stats.h5")}}, f)
+    return cfg, hcfg, sd, hsd, tstats, vstats, texts
+
+
+def test_reference_cli_reaches_the_matcha_class_and_there_is_no_cpu_path(tmp_path):
+    _write_matcha_files(tmp_path)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _run_cli(tmp_path, tmp_path / "out")
+
+
+def test_reference_cli_runs_matcha_to_the_end_with_our_objects(tmp_path):
+    import jatts_b200
+    from oracle import hifigan as ohg
+    from oracle import matcha as om
+    from oracle import recipes
+
+    cfg, hcfg, sd, hsd, tstats, vstats, texts = _write_matcha_files(tmp_path)
+    seen = {"kwargs": []}
+
+    def fake_matcha(self, texts_, spembs=None, n_timesteps=10, temperature=0.667, noise=None):
+        """stands in for the CUDA engine call ONLY; the noise is a seeded stream keyed by the utterance length"""
+        st = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        seen["kwargs"].append((n_timesteps, temperature))
+        return [om.matcha_inference(st, cfg, x.cpu(), recipes.make_noise(512, cfg["odim"], int(x.numel())).t(), n_timesteps, temperature)
+                for x in texts_]
+
+    def fake_hifigan(self, mels, normalize_before=False, pcm16=False):
+        st = {k: v.detach().cpu() for k, v in self.state_dict().items() if k not in ("mean", "scale")}
+        a, b = self._affine
+        return [ohg.hifigan_forward(st, hcfg, m.cpu() * a + b) for m in mels]
+
+    with mock.patch.object(jatts_b200.MatchaTTS, "inference_batch", fake_matcha), \
+            mock.patch.object(jatts_b200.HiFiGANGenerator, "inference_batch", fake_hifigan):
+        _run_cli(tmp_path, tmp_path / "out")
+    assert seen["kwargs"] == [(3, 0.667)] * len(texts), "the CLI did not pass ode_steps / temperature from the config"
+    for i, x in enumerate(texts):
+        ref = om.matcha_inference(sd, cfg, x, recipes.make_noise(512, cfg["odim"], int(x.numel())).t(), 3, 0.667)
         yref = ohg.vocoder_decode(hsd, hcfg, ref["feat_gen"], vstats, tstats)
         with wave.open(str(tmp_path / "out" / "wav" / f"utt{i}.wav"), "rb") as w:
             assert w.getframerate() == 24000 and w.getsampwidth() == 2
