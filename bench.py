@@ -678,7 +678,7 @@ def run_matcha64(args, rank: int, world: int, local_rank: int):
                      "note": "achieved counts each product once; the kernel issues 3 MMAs per product (frac_of_issued_mma)",
                      "matcha_attention": {"launches_per_step": int(t2m["attention"][1]), "kernel_ms_per_step": t2m["attention"][0]},
                      "matcha_norm_act": {"launches_per_step": int(t2m["layernorm"][1]), "kernel_ms_per_step": t2m["layernorm"][0],
-                                         "what": "LayerNorm, GroupNorm statistics + Mish, SnakeBeta"},
+                                         "what": "LayerNorm, GroupNorm statistics + Mish (SnakeBeta is an epilogue of its GEMM)"},
                      "hifigan_conv": {"launches_per_step": n_conv, "kernel_ms_per_step": ms_conv}},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "host_cpus": cpu_cores,
                          "sample": "2 of the 64 utterances (50 phonemes each) x 3 repetitions after 1 warm-up, per-utterance loop as "

@@ -14,7 +14,7 @@
 
 namespace jb {
 
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3, ACT_GLU = 4 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3, ACT_GLU = 4, ACT_SNAKE = 5 };
 
 struct ConvGemmEpilogue {
   const float* bias;        // [N] (GLU: [N_pad] permuted like the weights) or null
@@ -36,6 +36,10 @@ struct ConvGemmEpilogue {
   bf16* out_act;            // optional bf16(leaky_relu(v, out_act_slope))  (next conv's operand)
   float out_act_slope;
   int out_act_ld;
+  // ACT_SNAKE (SnakeBeta, jatts/modules/matchatts/transformer.py:28-102): x + sin(x * snake_a[n])^2 * snake_ib[n], tables of
+  // n_pad floats (a = exp(alpha), ib = 1 / (exp(beta) + 1e-9)); split GEMM with a single accumulation chain only
+  const float* snake_a;
+  const float* snake_ib;
 };
 
 struct ConvGemmProblem {

@@ -67,7 +67,8 @@ struct Params3 {
   int num_m_tiles, num_n_tiles;
   const uint8_t* frame_mask;
   const float* bias;
-  int act;          // ACT_NONE / ACT_RELU / ACT_TANH / ACT_GLU
+  int act;          // ACT_NONE / ACT_RELU / ACT_TANH / ACT_GLU / ACT_SNAKE
+  const float* sn_a; const float* sn_ib;   // ACT_SNAKE: per-column exp(alpha), 1 / (exp(beta) + 1e-9) (n_pad floats each)
   float scale;
   const float* res; int res_ld;          // fp32 residual added to the output (may alias out_f32)
   float* out_f32; int out_f32_ld;        // optional fp32 output
@@ -157,7 +158,8 @@ __device__ __forceinline__ void store_pass(const Params3& P, uint32_t stg, int p
 
 // PAIR: the two CTAs of a cluster issue M = 256 cta_group::2 MMAs; each keeps its own 128 activation rows and HALF of
 // every weight tile pair (a template parameter: kernels with cta_group::2 code need an even cluster size to launch)
-// ACTK: 0 = none / ReLU (a floor of -inf / 0: one code path), 1 = tanh, 2 = GLU -- a template parameter because the
+// ACTK: 0 = none / ReLU (a floor of -inf / 0: one code path), 1 = tanh, 2 = GLU, 3 = SnakeBeta (single-chain kernels
+// only) -- a template parameter because the
 // unrolled epilogue with a run-time activation switch compiled to 10 k instructions per kernel (instruction-cache bound)
 // SINGLE: every tile is one accumulation chain (K <= 8 blocks: the projections and pointwise convolutions, 4.6 k clk of
 // MMAs per tile).  Four epilogue warps issue one dependent instruction stream per scheduler and need 11-12 k clk per
@@ -392,10 +394,23 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
               }
             } else {
 #pragma unroll
+              float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+              if constexpr (ACTK == 3) {   // warp-uniform addresses: one broadcast transaction each, L1 resident
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.sn_a + n0 + tc + 4 * q));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.sn_ib + n0 + tc + 4 * q));
+                sa[0] = a4.x; sa[1] = a4.y; sa[2] = a4.z; sa[3] = a4.w;
+                sb[0] = b4.x; sb[1] = b4.y; sb[2] = b4.z; sb[3] = b4.w;
+              }
+#pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float x = fmaf(__uint_as_float(c[4 * q + i]), 1.0f / kSplitScale, __uint_as_float(m[4 * q + i])) + bv[i];
                 if constexpr (ACTK == 1) x = tanhf(x);
-                else x = fmaxf(x, act_floor);
+                else if constexpr (ACTK == 3) {
+                  // sin.approx after the hardware range reduction: |error| <= 2^-21 + |arg| * 2^-24 (args here are O(10)),
+                  // two instructions instead of the ~40 of sinf, which made this epilogue the bound of the GEMM
+                  const float t = __sinf(x * sa[i]);
+                  x = fmaf(sb[i], t * t, x);
+                } else x = fmaxf(x, act_floor);
                 v[i] = x * P.scale;
               }
             }
@@ -528,7 +543,10 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 bool conv_gemm_tc3_eligible(const ConvGemmProblem& p) {
   const ConvGemmEpilogue& e = p.ep;
   if (!p.a_lo || !p.w_lo || p.up_s > 0 || p.block_n != BN || p.w_tap_stride != 0) return false;
-  if (!(e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_TANH || e.act == ACT_GLU)) return false;
+  if (!(e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_TANH || e.act == ACT_GLU || e.act == ACT_SNAKE)) return false;
+  if (e.act == ACT_SNAKE && (!e.snake_a || !e.snake_ib || p.taps * ceil_div(p.a_cols > 0 ? p.a_cols : p.k_pad, BK) > CHUNK ||
+                             p.n != p.n_pad))
+    return false;   // SnakeBeta lives in the single-chain epilogue only
   if (e.res_bf16 || e.accum_in || e.accum_bf16 || e.out_act || e.res_inv_slope != 0.f) return false;
   if ((e.out_hi != nullptr) != (e.out_lo != nullptr)) return false;
   if (e.post_scale != 1.0f) return false;
@@ -571,6 +589,7 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.frame_mask = p.frame_mask;
   kp.bias = e.bias;
   kp.act = e.act;
+  kp.sn_a = e.snake_a; kp.sn_ib = e.snake_ib;
   kp.scale = e.scale;
   kp.res = e.res_f32; kp.res_ld = e.res_ld;
   kp.out_f32 = e.out_f32; kp.out_f32_ld = e.out_f32_ld;
@@ -585,16 +604,19 @@ int conv_gemm_tc3(const ConvGemmProblem& p, cudaStream_t stream) {
   static const int env_dbg = getenv("JATTS_B200_TC3_DEBUG") ? atoi(getenv("JATTS_B200_TC3_DEBUG")) : 0;
   kp.dbg = env_dbg;
   const int smem_bytes = smem_fixed(kp.b_stages);
-  const int actk = e.act == ACT_GLU ? 2 : (e.act == ACT_TANH ? 1 : 0);
+  const int actk = e.act == ACT_GLU ? 2 : (e.act == ACT_TANH ? 1 : (e.act == ACT_SNAKE ? 3 : 0));
   // single-chain launches (K <= 8 blocks) run the 12-warp kernel with two epilogue groups
   const int single = kp.taps * kp.k_chunks <= CHUNK ? 1 : 0;
   using KernFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params3);
-  static const KernFn kerns[2][2][3] = {
-      {{gemm_split_tma_kernel<false, 0, false>, gemm_split_tma_kernel<false, 1, false>, gemm_split_tma_kernel<false, 2, false>},
-       {gemm_split_tma_kernel<true, 0, false>, gemm_split_tma_kernel<true, 1, false>, gemm_split_tma_kernel<true, 2, false>}},
-      {{gemm_split_tma_kernel<false, 0, true>, gemm_split_tma_kernel<false, 1, true>, gemm_split_tma_kernel<false, 2, true>},
-       {gemm_split_tma_kernel<true, 0, true>, gemm_split_tma_kernel<true, 1, true>, gemm_split_tma_kernel<true, 2, true>}}};
+  static const KernFn kerns[2][2][4] = {
+      {{gemm_split_tma_kernel<false, 0, false>, gemm_split_tma_kernel<false, 1, false>, gemm_split_tma_kernel<false, 2, false>, nullptr},
+       {gemm_split_tma_kernel<true, 0, false>, gemm_split_tma_kernel<true, 1, false>, gemm_split_tma_kernel<true, 2, false>, nullptr}},
+      {{gemm_split_tma_kernel<false, 0, true>, gemm_split_tma_kernel<false, 1, true>, gemm_split_tma_kernel<false, 2, true>,
+        gemm_split_tma_kernel<false, 3, true>},
+       {gemm_split_tma_kernel<true, 0, true>, gemm_split_tma_kernel<true, 1, true>, gemm_split_tma_kernel<true, 2, true>,
+        gemm_split_tma_kernel<true, 3, true>}}};
   const KernFn kern = kerns[single][pair ? 1 : 0][actk];
+  JB_REQUIRE(kern != nullptr, -1, "conv_gemm_tc3: SnakeBeta needs a single accumulation chain (K <= 512)");
   JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_bytes));
   const int units = pair ? kp.num_groups : kp.num_m_tiles * kp.num_n_tiles;
   if (units == 0) return 0;

@@ -83,9 +83,6 @@ int output_conv_tanh(const bf16* x, int ld, int c, const float* w /*[k][c]*/, fl
 // nseg * groups float2; outputs (each optional): y fp32, hi/lo operand pair whose gap rows are written as zeros
 int groupnorm_mish_rows(const float* x, int c, int groups, const float* gamma, const float* beta, float eps, const float* add,
                         RowLayout L, float2* stats, float* y, bf16* hi, bf16* lo, int bf_ld, cudaStream_t s);
-// SnakeBeta after its Linear (transformer.py:28-102): x + sin(x * a)^2 * ib, a = exp(alpha), ib = 1 / (exp(beta) + 1e-9)
-int snake_beta_rows(const float* x, int c, const float* a, const float* ib, RowLayout L, bf16* hi, bf16* lo, int bf_ld,
-                    cudaStream_t s);
 // utterance-contiguous fp32 [sum T, c] * scale -> packed fp32 rows + operand pair (gap rows of the pair zeroed)
 int pack_rows_split(const float* in, int c, float scale, RowLayout L, const int* off, float* y, int y_ld, bf16* hi, bf16* lo,
                     int bf_ld, cudaStream_t s);
