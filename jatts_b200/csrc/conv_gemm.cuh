@@ -68,6 +68,12 @@ struct ConvGemmProblem {
   int w_row0, w_tap_stride, w_rows_total;
   int store_row_off, out_pitch_mul, out_view_rows;
   int mask_mul, mask_add;
+  // ALL phases of the polyphase transposed convolution in ONE launch (conv_gemm_tc2 only): phases > 0 = up-sampling factor s,
+  // phase_pp = its padding p.  Phase q is the N tile q (block_n == n == C_out): weight rows w_row0 + t*w_tap_stride + q*n,
+  // tap_off0 = q >= p ? -1 : 0, output rows first(q) + r*s with first(q) = q >= p ? q - p : q - p + s in a view of pitch s rows
+  // (out_act = the tensor's base; out_pitch_mul = mask_mul = s; out_view_rows / mask_add / tap_off0 / store_row_off unused).
+  // Units are walked M-tile major, so the s phases of an M tile run at the same time and its activation slab leaves HBM once.
+  int phases, phase_pp;
   ConvGemmEpilogue ep;
 };
 

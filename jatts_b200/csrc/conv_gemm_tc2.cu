@@ -57,6 +57,8 @@ struct KernelParams2 {
   int w_row0, w_tap_stride;       // weight rows of tap t: w_row0 + t*w_tap_stride (+ n0)
   int store_row_off;              // output row coordinate = m0 + store_row_off
   int mask_mul, mask_add, out_rows;  // validity: frame_mask[(row*mask_mul + mask_add) / rate], 0 <= . < out_rows
+  int n_phases, phase_pp;            // > 0: N tile q is phase q of a polyphase transposed convolution (ConvGemmProblem::phases):
+                                     // tap_off0, mask_add and the output tensor map depend on q
   long long* trace; // debug: per-role clock64 timeline of CTA 0 (jatts_debug_set_trace), else null
 };
 
@@ -143,7 +145,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                      const __grid_constant__ CUtensorMap tm_bm,
                      const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_acc,
                      const __grid_constant__ CUtensorMap tm_out0, const __grid_constant__ CUtensorMap tm_out1,
-                     const __grid_constant__ KernelParams2 P) {
+                     const __grid_constant__ CUtensorMap tm_ph4, const __grid_constant__ KernelParams2 P) {
   using C = Cfg2<BLOCK_N, KCH, MODE>;
   constexpr int STAGES = C::STAGES;
   constexpr int KSTEPS = KCH / UMMA_K2;
@@ -184,6 +186,11 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   const int cid = static_cast<int>(blockIdx.x) / cl;
   const int ncl = static_cast<int>(gridDim.x) / cl;
   const uint16_t cl_mask = static_cast<uint16_t>((1u << cl) - 1u);
+  // phase mode: per-phase tap offset / first output row / output view (the five tensor-map slots hold phases 0..4)
+  const int n_ph = P.n_phases;
+  auto tap_off_of = [&](int q) { return n_ph ? (q >= P.phase_pp ? -1 : 0) : P.tap_off0; };
+  auto mask_add_of = [&](int q) { return n_ph ? (q >= P.phase_pp ? q - P.phase_pp : q - P.phase_pp + n_ph) : P.mask_add; };
+  const CUtensorMap* const ph_maps[5] = {&tm_out1, &tm_out0, &tm_res, &tm_acc, &tm_ph4};
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -192,6 +199,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (P.has_acc) tma_prefetch_desc(&tm_acc);
     if (P.has_out0) tma_prefetch_desc(&tm_out0);
     if (P.has_out1) tma_prefetch_desc(&tm_out1);
+    for (int q = 1; q < n_ph; ++q) tma_prefetch_desc(ph_maps[q]);
     for (int i = 0; i < NB; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], (MODE == MODE_HALO && !PAIR) ? cl : 1);   // multicast weight stage: freed by every CTA of the cluster
@@ -251,7 +259,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         const int n0 = (grp % P.num_n_tiles) * BLOCK_N;
         if (MODE == MODE_STREAM) {
           for (int tap = 0; tap < P.taps; ++tap) {
-            const int arow = m0 + P.tap_off0 + tap * P.tap_stride;
+            const int arow = m0 + tap_off_of(grp % P.num_n_tiles) + tap * P.tap_stride;
             const int brow = P.w_row0 + tap * P.w_tap_stride + n0;
             for (int kc = 0; kc < P.k_chunks; ++kc) {
               mbar_wait(&empty_bar[rs.idx], rs.phase ^ 1);
@@ -268,12 +276,12 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             if (kc == 0) JB_TRACE(0, 0, seq);
             if constexpr (!PAIR) {
               mbar_expect_tx(&afull_bar[ra.idx], a_bytes);
-              tma_load_2d(&tm_a, &afull_bar[ra.idx], smem + ra.idx * C::A_SLAB_BYTES, kc * KCH, m0 + P.tap_off0);
+              tma_load_2d(&tm_a, &afull_bar[ra.idx], smem + ra.idx * C::A_SLAB_BYTES, kc * KCH, m0 + tap_off_of(grp % P.num_n_tiles));
             } else {
               // both CTAs' slabs complete on the LEADER's barrier (only the leader's MMA thread waits on it)
               if (rank == 0) mbar_expect_tx(&afull_bar[ra.idx], 2 * a_bytes);
               tma_load_2d_pair(&tm_a, mapa_u32(smem_u32(&afull_bar[ra.idx]), 0), smem + ra.idx * C::A_SLAB_BYTES, kc * KCH,
-                               m0 + P.tap_off0);
+                               m0 + tap_off_of(grp % P.num_n_tiles));
             }
             ra.next();
             if (MODE == MODE_HALO) {
@@ -438,8 +446,12 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           re.next();
           if (s == 0) JB_TRACE(3, 0, seq);
           uint8_t* bufA = ep_base + e * entry_bytes;
-          if (P.has_out0) tma_store_2d(&tm_out0, bufA, n0 + s * C::SLAB, m0 + P.store_row_off);
-          if (P.has_out1) tma_store_2d(&tm_out1, bufA + (P.ep_bufs - 1) * C::SLAB_BYTES, n0 + s * C::SLAB, m0 + P.store_row_off);
+          if (n_ph) {   // phase q's strided output view; its columns are the phase's own C_out channels
+            tma_store_2d(ph_maps[grp % P.num_n_tiles], bufA + (P.ep_bufs - 1) * C::SLAB_BYTES, s * C::SLAB, m0);
+          } else {
+            if (P.has_out0) tma_store_2d(&tm_out0, bufA, n0 + s * C::SLAB, m0 + P.store_row_off);
+            if (P.has_out1) tma_store_2d(&tm_out1, bufA + (P.ep_bufs - 1) * C::SLAB_BYTES, n0 + s * C::SLAB, m0 + P.store_row_off);
+          }
           tma_store_commit();
           ++groups;
           // `depth` older store groups stay in flight; the entry of the group that has certainly finished
@@ -477,7 +489,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       if (grp >= P.num_groups) return 0u;
       const int row = ((grp / P.num_n_tiles) * cl + rank) * BLOCK_M2 + row_in_tile;
       if (row >= P.m_rows) return 0u;
-      const long long orow = static_cast<long long>(row) * P.mask_mul + P.mask_add;
+      const long long orow = static_cast<long long>(row) * P.mask_mul + mask_add_of(grp % P.num_n_tiles);
       if (orow < 0 || orow >= P.out_rows) return 0u;
       return P.frame_mask ? static_cast<unsigned>(__ldg(P.frame_mask + orow / P.rate)) : 1u;
     };
@@ -522,7 +534,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
         uint8_t* bufA = ep_base + e * entry_bytes;
         uint8_t* bufB = bufA + (P.ep_bufs - 1) * C::SLAB_BYTES;   // == bufA when an entry is a single slab
-        const uint32_t bs_addr = smem_u32(bias_s) + static_cast<uint32_t>(n0 + s * C::SLAB + half * CW) * 4u;
+        const uint32_t bs_addr = smem_u32(bias_s) + static_cast<uint32_t>((n_ph ? 0 : n0) + s * C::SLAB + half * CW) * 4u;
 #pragma unroll
         for (int c = 0; c < CW / 8; ++c) {
           const uint32_t off = row_off + ((static_cast<uint32_t>(half * (CW / 8) + c) ^ sw) << 4);
@@ -617,6 +629,12 @@ bool conv_gemm_tc2_eligible(const ConvGemmProblem& p) {
   if (!ok(e.res_bf16, e.res_ld) || !ok(e.accum_bf16, e.res_ld) || !ok(e.out_hi, e.out_bf_ld) || !ok(e.out_act, e.out_act_ld))
     return false;
   if (!e.out_hi && !e.out_act) return false;
+  if (p.phases != 0) {   // all phases of a transposed convolution in one launch
+    if (p.phases < 2 || p.phases > 5 || p.phase_pp < 0 || p.phase_pp >= p.phases || !phase || p.n != p.block_n || p.taps != 2 ||
+        p.tap_stride != 1 || e.res_bf16 || e.accum_bf16 || e.out_hi || !e.out_act || p.out_pitch_mul != p.phases ||
+        p.mask_mul != p.phases)
+      return false;
+  }
   (void)slab;
   return true;
 }
@@ -626,7 +644,7 @@ template <int BLOCK_N, int KCH, int MODE, bool PAIR = false>
 static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   using C = Cfg2<BLOCK_N, KCH, MODE>;
   const ConvGemmEpilogue& e = p.ep;
-  CUtensorMap ta, tb, tbm, tres, tacc, to0, to1;
+  CUtensorMap ta, tb, tbm, tres, tacc, to0, to1, tph4;
   const int a_cols = p.a_cols > 0 ? p.a_cols : p.k_pad;
   const int k_chunks = ceil_div(a_cols, KCH);   // channel padding beyond a_cols is all-zero: skip it
   const int halo_rows = round_up(BLOCK_M2 + (p.taps - 1) * p.tap_stride, 8);
@@ -645,13 +663,25 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   else if (MODE == MODE_HALO && (env_cl == 2 || env_cl == 4) && ceil_div(p.m_rows, BLOCK_M2) >= 2 * env_cl) cl = env_cl;
   tbm = tb;
   if (cl > 1) JB_PROPAGATE(make_tmap(&tbm, p.w_hi, w_rows, p.k_pad, p.k_pad, BLOCK_N / cl, KCH));
-  tres = tacc = to0 = to1 = ta;
+  tres = tacc = to0 = to1 = tph4 = ta;
   if (e.res_bf16) JB_PROPAGATE(make_tmap(&tres, e.res_bf16, p.m_rows, p.n, e.res_ld, BLOCK_M2, C::SLAB));
   if (e.accum_bf16) JB_PROPAGATE(make_tmap(&tacc, e.accum_bf16, p.m_rows, p.n, e.res_ld, BLOCK_M2, C::SLAB));
   const int pitch_mul = p.out_pitch_mul > 0 ? p.out_pitch_mul : 1;
   const long long view_rows = p.out_pitch_mul > 0 ? p.out_view_rows : p.m_rows;
   if (e.out_hi) JB_PROPAGATE(make_tmap(&to0, e.out_hi, view_rows, p.n, e.out_bf_ld * pitch_mul, BLOCK_M2, C::SLAB));
-  if (e.out_act) JB_PROPAGATE(make_tmap(&to1, e.out_act, view_rows, p.n, e.out_act_ld * pitch_mul, BLOCK_M2, C::SLAB));
+  if (e.out_act && p.phases == 0)
+    JB_PROPAGATE(make_tmap(&to1, e.out_act, view_rows, p.n, e.out_act_ld * pitch_mul, BLOCK_M2, C::SLAB));
+  if (p.phases > 0) {
+    // phase q stores to every s-th row starting at first(q): one strided view per phase, in the slots the kernel's
+    // ph_maps[] names (out1, out0, res, acc, ph4)
+    CUtensorMap* slots[5] = {&to1, &to0, &tres, &tacc, &tph4};
+    for (int q = 0; q < p.phases; ++q) {
+      const long long first = q >= p.phase_pp ? q - p.phase_pp : q - p.phase_pp + p.phases;
+      const long long rows_q = (static_cast<long long>(p.out_rows) - first + p.phases - 1) / p.phases;
+      JB_PROPAGATE(make_tmap(slots[q], e.out_act + first * e.out_act_ld, rows_q > 0 ? rows_q : 1, p.n, e.out_act_ld * p.phases,
+                             BLOCK_M2, C::SLAB));
+    }
+  }
   KernelParams2 kp;
   kp.taps = p.taps;
   kp.k_chunks = k_chunks;
@@ -660,7 +690,9 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.tap_stride = p.tap_stride;
   kp.m_rows = p.m_rows;
   kp.num_m_tiles = ceil_div(p.m_rows, BLOCK_M2);
-  kp.num_n_tiles = (p.w_tap_stride != 0 ? p.n : p.n_pad) / BLOCK_N;
+  kp.num_n_tiles = p.phases > 0 ? p.phases : (p.w_tap_stride != 0 ? p.n : p.n_pad) / BLOCK_N;
+  kp.n_phases = p.phases;
+  kp.phase_pp = p.phase_pp;
   kp.cl = cl;
   kp.pair = pair;
   kp.num_groups = ceil_div(kp.num_m_tiles, cl) * kp.num_n_tiles;
@@ -676,6 +708,8 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.has_acc = e.accum_bf16 != nullptr;
   kp.has_out0 = e.out_hi != nullptr;
   kp.has_out1 = e.out_act != nullptr;
+  JB_REQUIRE(p.phases == 0 || (!kp.has_res && !kp.has_acc && !kp.has_out0 && kp.has_out1 && MODE != MODE_RESIDENT), -2,
+             "conv_gemm_tc2: phase mode takes a plain convolution with one activated output and streamed weights");
   kp.halo_rows = halo_rows;
   kp.w_row0 = p.w_row0;
   kp.w_tap_stride = p.w_tap_stride != 0 ? p.w_tap_stride : p.n_pad;
@@ -727,7 +761,7 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
     JB_CUDA_OK(cudaEventCreate(&e1));
     JB_CUDA_OK(cudaEventRecord(e0, stream));
   }
-  JB_CUDA_OK(launch_tc(kern, grid, kThreads2, smem_bytes, stream, cl, ta, tb, tbm, tres, tacc, to0, to1, kp));
+  JB_CUDA_OK(launch_tc(kern, grid, kThreads2, smem_bytes, stream, cl, ta, tb, tbm, tres, tacc, to0, to1, tph4, kp));
   JB_KERNEL_OK();
   if (g_profile_on) {
     JB_CUDA_OK(cudaEventRecord(e1, stream));
@@ -743,7 +777,7 @@ int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream) {
                        round_up(BLOCK_M2 + (p.taps - 1) * p.tap_stride, 8) <= 192;
   // RESIDENT when every weight tile of the convolution fits next to the pipeline buffers
   auto resident_ok = [&](int fixed, int b_bytes, int kch) {
-    return halo_ok && max_mode >= MODE_RESIDENT && (p.w_tap_stride != 0 ? p.n : p.n_pad) == p.block_n &&
+    return p.phases == 0 && halo_ok && max_mode >= MODE_RESIDENT && (p.w_tap_stride != 0 ? p.n : p.n_pad) == p.block_n &&
            fixed + round_up(p.taps * ceil_div(a_cols, kch) * b_bytes, 1024) + 4 * 2 * 8192 <= 227 * 1024;
   };
   // CTA pairs (cta_group::2, M = 256): each SM reads and is sent half of every weight tile, which takes the
@@ -756,10 +790,12 @@ int conv_gemm_tc2(const ConvGemmProblem& p, cudaStream_t stream) {
         return launch2<32, 32, MODE_RESIDENT>(p, stream);
       if (resident_ok(Cfg2<32, 64, MODE_RESIDENT>::SMEM_FIXED, Cfg2<32, 64, MODE_RESIDENT>::B_BYTES, 64))
         return launch2<32, 64, MODE_RESIDENT>(p, stream);
+      if (p.phases > 0 && halo_ok) return launch2<32, 64, MODE_HALO>(p, stream);
       return launch2<32, 64, MODE_STREAM>(p, stream);
     case 64:
       if (resident_ok(Cfg2<64, 64, MODE_RESIDENT>::SMEM_FIXED, Cfg2<64, 64, MODE_RESIDENT>::B_BYTES, 64))
         return launch2<64, 64, MODE_RESIDENT>(p, stream);
+      if (p.phases > 0 && halo_ok) return launch2<64, 64, MODE_HALO>(p, stream);
       return launch2<64, 64, MODE_STREAM>(p, stream);
     case 128:
       if (resident_ok(Cfg2<128, 64, MODE_RESIDENT>::SMEM_FIXED, Cfg2<128, 64, MODE_RESIDENT>::B_BYTES, 64))

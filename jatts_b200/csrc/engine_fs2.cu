@@ -166,8 +166,14 @@ static int zero_operand_gaps(jatts_fs2* h, const RowLayout& L, cudaStream_t s) {
                                             {h->c_lo, d}, {h->p_hi, pc}, {h->p_lo, pc}, {h->b_hi, od_pad},
                                             {h->b_lo, od_pad}, {h->pa_hi, pn}, {h->pa_lo, pn}, {h->pb_hi, pn},
                                             {h->pb_lo, pn}};
-  for (auto& b : bufs) JB_PROPAGATE(zero_gap_rows(b.p, b.cols * 2, L, 1, s));
-  return 0;
+  void* ptrs[16];
+  int bytes[16];
+  int n = 0;
+  for (auto& b : bufs) {
+    ptrs[n] = b.p;
+    bytes[n++] = b.cols * 2;
+  }
+  return zero_gap_rows_multi(ptrs, bytes, n, L, s);   // one launch instead of 14
 }
 
 // out = epilogue(conv(A)) with "same" padding over the packed layout

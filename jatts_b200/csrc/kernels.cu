@@ -31,23 +31,32 @@ int fill_layout(const int* seg_start, const int* seg_len, int nseg, int n_rows, 
   return 0;
 }
 
-// grid = (gap rows per utterance at this rate, utterances): only the rows that must be zero are touched
-__global__ void zero_gap_rows_kernel(uint4* __restrict__ buf, int row_vec, const int* __restrict__ seg_start,
-                                     const int* __restrict__ seg_len, int rate) {
-  const int b = blockIdx.y;
-  const long long r = (static_cast<long long>(seg_start[b]) + seg_len[b]) * rate + blockIdx.x;
-  uint4* p = buf + r * row_vec;
-  for (int i = threadIdx.x; i < row_vec; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+// grid = (gap rows per utterance, utterances, buffers): only the rows that must be zero are touched; up to 16 buffers in
+// one launch (the engines zero ~14 operand buffers per layout)
+struct GapBufs {
+  uint4* p[16];
+  int row_vec[16];
+};
+__global__ void zero_gap_rows_multi_kernel(GapBufs B, const int* __restrict__ seg_start, const int* __restrict__ seg_len) {
+  const int b = blockIdx.y, k = blockIdx.z;
+  const long long r = static_cast<long long>(seg_start[b]) + seg_len[b] + blockIdx.x;
+  const int rv = B.row_vec[k];
+  uint4* p = B.p[k] + r * rv;
+  for (int i = threadIdx.x; i < rv; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
 }
-int zero_gap_rows(void* buf, int row_bytes, RowLayout L, int rate, cudaStream_t s) {
-  JB_REQUIRE(row_bytes % 16 == 0, -2, "zero_gap_rows: row_bytes % 16");
-  if (L.nseg == 0) return 0;
-  dim3 grid(kGapRows * rate, L.nseg);
-  zero_gap_rows_kernel<<<grid, 64, 0, s>>>(static_cast<uint4*>(buf), row_bytes / 16, L.seg_start, L.seg_len, rate);
+int zero_gap_rows_multi(void* const* bufs, const int* row_bytes, int n, RowLayout L, cudaStream_t s) {
+  JB_REQUIRE(n >= 0 && n <= 16, -2, "zero_gap_rows_multi: at most 16 buffers");
+  if (L.nseg == 0 || n == 0) return 0;
+  GapBufs B{};
+  for (int i = 0; i < n; ++i) {
+    JB_REQUIRE(row_bytes[i] % 16 == 0, -2, "zero_gap_rows_multi: row_bytes % 16");
+    B.p[i] = static_cast<uint4*>(bufs[i]);
+    B.row_vec[i] = row_bytes[i] / 16;
+  }
+  zero_gap_rows_multi_kernel<<<dim3(kGapRows, L.nseg, n), 64, 0, s>>>(B, L.seg_start, L.seg_len);
   JB_KERNEL_OK();
   return 0;
 }
-
 // ------------------------------------------------------------------------------------------------
 // embedding
 // ------------------------------------------------------------------------------------------------

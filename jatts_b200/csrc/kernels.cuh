@@ -7,8 +7,8 @@ namespace jb {
 // layout: fill frame_mask / frame_seg for n_rows rows from seg_start/seg_len (device arrays)
 int fill_layout(const int* seg_start, const int* seg_len, int nseg, int n_rows, uint8_t* frame_mask, int* frame_seg,
                 cudaStream_t s);
-// zero the kGapRows*rate rows that follow every utterance of a [n_rows*rate, row_bytes] buffer (row_bytes % 16 == 0)
-int zero_gap_rows(void* buf, int row_bytes, RowLayout L, int rate, cudaStream_t s);
+// zero the kGapRows rows that follow every utterance of up to 16 [n_rows, row_bytes] buffers (row_bytes % 16 == 0), one launch
+int zero_gap_rows_multi(void* const* bufs, const int* row_bytes, int n, RowLayout L, cudaStream_t s);
 
 // x[row,:] = emb[token,:] * scale for valid rows (fastspeech2.py:270-272 + positional_encoding.py:233)
 int embed_tokens(const long long* tokens, const int* tok_off, const float* emb, int vocab, int d, float scale,

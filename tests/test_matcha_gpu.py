@@ -52,6 +52,17 @@ def test_small_model_batch_rows_equal_per_utterance_oracle(steps):
 
 
 @pytest.mark.gpu
+def test_long_and_short_utterances_in_one_batch():
+    """~900 frames next to ~20: several 127-row attention tiles at both rates, GroupNorm statistics over long rows, and the
+    per-utterance boundaries of every convolution in between"""
+    model, sd, cfg = get_model("SMALL_MATCHA", 1)
+    texts = [recipes.make_phonemes(t, 140 + i, cfg["idim"]) for i, t in enumerate([150, 3, 64])]
+    err = run_and_compare(model, sd, cfg, texts, 2, 0.667, seed=77)
+    print(f"long / short batch: mel max-abs error {err:.3e}")
+    assert err < 1e-3, err
+
+
+@pytest.mark.gpu
 def test_single_utterance_inference_signature_and_batch_independence():
     model, sd, cfg = get_model("SMALL_MATCHA", 1)
     xs = [recipes.make_phonemes(t, 60 + i, cfg["idim"]) for i, t in enumerate([9, 4, 15])]
