@@ -10,7 +10,7 @@ full() {  # name, step part, kernel regex, skip
 }
 full pair_c32_k11 voc mrf_pair_kernel 16
 full pair_c64_k7 voc mrf_pair_kernel 4
-full conv_c128_k11 voc conv_bf16_tma_kernel 38
+full conv_c128_k11 voc conv_bf16_tma_kernel 30
 full gemm_split_ffn1 fs2 gemm_split 41
 full gemm_split_qkv fs2 gemm_split 44
 full attention_dec fs2 relpos_attention 5
