@@ -242,6 +242,26 @@ def pack_hifigan(sd: dict, cfg: dict, mel_scale: torch.Tensor, mel_shift: torch.
         tap0 = w[:, :, :s].permute(2, 1, 0).reshape(s * co, ci)
         tap1 = w[:, :, s:].permute(2, 1, 0).reshape(s * co, ci)
         pack_taps(torch.stack([tap0, tap1], 0), False, out, f"ups{i}", sd[f"upsamples.{i}.1.bias"])
+        if s * co <= 128:
+            # narrow last stage(s): the WHOLE transposed convolution as one 3-tap convolution with N = s * C_out, output
+            # row i = frames i*s .. i*s + s - 1 side by side (contiguous in the channels-last output).  Output frame i*s + r
+            # has kernel index k = r + p (mod s): r + p < s -> x[i] w_k + x[i-1] w_{k+s}; else x[i+1] w_{k-s}... i.e.
+            # with q = (r + p) % s: class A (r < s - p) taps (-1, 0) = (w_{q+s}, w_q), class B taps (0, +1) = (w_{q+s}, w_q).
+            # One N = 128 tile per input tile instead of s tiles of N = C_out: the tiles of this stage are too small to pay
+            # for their own pipeline hand-offs (measured 248 us for three phases of 1.96 M rows x 64 -> 32 channels)
+            pp = s // 2 + s % 2
+            t3 = torch.zeros(3, 128, ci)      # N padded to ONE 128-wide tile (pick_block_n would cut 96 into 3 x 32)
+            for r in range(s):
+                q = (r + pp) % s
+                w_lo, w_hi = w[:, :, q].t(), w[:, :, q + s].t()          # [C_out, C_in]
+                blk = slice(r * co, (r + 1) * co)
+                if r < s - pp:
+                    t3[0, blk], t3[1, blk] = w_hi, w_lo
+                else:
+                    t3[1, blk], t3[2, blk] = w_hi, w_lo
+            bias = torch.zeros(128)
+            bias[:s * co] = sd[f"upsamples.{i}.1.bias"].float().repeat(s)
+            pack_taps(t3, False, out, f"ups{i}.t3", bias)
         for j in range(nb):
             for d in range(len(cfg["resblock_dilations"][j])):
                 b = f"blocks.{i * nb + j}."

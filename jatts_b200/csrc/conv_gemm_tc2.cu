@@ -622,7 +622,10 @@ bool conv_gemm_tc2_eligible(const ConvGemmProblem& p) {
   if (e.scale != 1.0f) return false;
   if (e.res_inv_slope != 0.f && !e.res_bf16) return false;
   const bool phase = p.w_tap_stride != 0;
-  if ((!phase && p.n != p.n_pad) || p.n > 512 || p.n % p.block_n != 0) return false;
+  // n < n_pad (one partly filled N tile): the output tensor map has n columns, so the TMA stores of the padding slabs
+  // are clipped; the weight rows and bias entries beyond n are zero (the narrow transposed convolutions, N = 96 of 128)
+  const bool partial_tile = !phase && p.n < p.n_pad && p.n_pad == p.block_n && p.n % 32 == 0 && !e.res_bf16 && !e.accum_bf16;
+  if ((!phase && p.n != p.n_pad && !partial_tile) || p.n > 512 || (p.n % p.block_n != 0 && !partial_tile)) return false;
   if (!phase && p.out_rows != p.m_rows) return false;
   const int slab = p.block_n >= 64 ? 64 : 32;
   auto ok = [&](const void* ptr, int ld) { return ptr == nullptr || (ld % 8 == 0 && ld >= p.n && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0); };

@@ -17,7 +17,7 @@ struct jatts_hifigan {
   int device = 0;
   WeightTable wt;
   ConvW input_conv;
-  std::vector<ConvW> ups;
+  std::vector<ConvW> ups, ups3;   // ups3: narrow stages as one 3-tap convolution (hi == null: not available)
   std::vector<std::vector<std::vector<ConvW>>> c1, c2;  // [stage][block][dilation]
   std::vector<std::vector<float>> host_bias;            // host copies of the residual-unit biases (ConvW::h_bias)
   const float *out_w, *mel_scale, *mel_shift;
@@ -131,6 +131,7 @@ extern "C" int jatts_hifigan_create(const jatts_hifigan_config* cfg, const jatts
   if ((rc = load_conv(h->wt, "input_conv", cfg->kernel_size, cfg->channels, cfg->in_channels, false, true, cfg->channels, &h->input_conv))) return fail(rc);
   int r = 1;
   h->ups.resize(cfg->n_upsamples);
+  h->ups3.resize(cfg->n_upsamples);
   h->c1.resize(cfg->n_upsamples);
   h->c2.resize(cfg->n_upsamples);
   for (int i = 0; i < cfg->n_upsamples; ++i) {
@@ -141,6 +142,10 @@ extern "C" int jatts_hifigan_create(const jatts_hifigan_config* cfg, const jatts
     h->rate.push_back(r);
     h->chans.push_back(co);
     if ((rc = load_conv(h->wt, "ups" + std::to_string(i), 2, s * co, ci, false, true, s * co, &h->ups[i]))) return fail(rc);
+    // narrow stages also come as ONE 3-tap convolution with N = s * C_out (<= 128) columns (_pack.py::pack_hifigan)
+    if (s * co <= 128 && h->wt.has("ups" + std::to_string(i) + ".t3.hi")) {
+      if ((rc = load_conv(h->wt, "ups" + std::to_string(i) + ".t3", 3, 128, ci, false, true, s * co, &h->ups3[i]))) return fail(rc);
+    }
     h->c1[i].resize(cfg->n_resblocks);
     h->c2[i].resize(cfg->n_resblocks);
     for (int j = 0; j < cfg->n_resblocks; ++j) {
@@ -286,11 +291,33 @@ static int hifigan_run_impl(jatts_hifigan* h, const float* d_mel, const int32_t*
       // activation slab leaves HBM once instead of s times; measured on the hop-300 generator: 17 launches -> 4,
       // convolution family 10.77 -> 10.6 ms per 64-utterance step), or -- scale > 5 (the canonical hop-256 V1 has 8)
       // or C_out > 256 -- one launch per phase
+      bool done = false;
+      if (h->ups3[i].hi != nullptr) {
+        // narrow stage: the whole transposed convolution as one 3-tap convolution whose output row i is frames
+        // i*s .. i*s + s - 1 (N = s * C_out <= 128: one tile per input tile; the phase tiles of N = C_out were too
+        // small to pay for their own pipeline hand-offs)
+        const ConvW& w3 = h->ups3[i];
+        ConvGemmProblem p{};
+        p.a_hi = h->y[cur]; p.a_rows = static_cast<int>(in_io.rows); p.a_ld = c_in; p.a_cols = c_in;
+        p.w_hi = w3.hi; p.taps = 3; p.n_pad = w3.n_pad; p.k_pad = w3.k_pad;
+        p.tap_off0 = -1; p.tap_stride = 1;
+        p.n = sc * co; p.m_rows = static_cast<int>(in_io.rows); p.block_n = w3.block_n;
+        p.frame_mask = h->mask; p.rate = in_io.rate; p.out_rows = static_cast<int>(in_io.rows);
+        ConvGemmEpilogue e{};
+        e.bias = w3.bias; e.scale = 1.f; e.post_scale = 1.f;
+        e.out_act = h->xa0; e.out_act_slope = slope; e.out_act_ld = sc * co;
+        p.ep = e;
+        if (conv_gemm_tc2_eligible(p)) {
+          JB_PROPAGATE(conv_gemm_tc2(p, s));
+          done = true;
+        }
+      }
       ConvGemmProblem all = phase_problem(0);
       all.phases = sc; all.phase_pp = pp;
       all.w_row0 = w.n_pad; all.tap_off0 = 0; all.mask_add = 0; all.out_view_rows = 0;
       all.ep.out_act = h->xa0;
-      if (co <= 256 && sc >= 2 && sc <= 5 && conv_gemm_tc2_eligible(all)) {
+      if (done) {
+      } else if (co <= 256 && sc >= 2 && sc <= 5 && conv_gemm_tc2_eligible(all)) {
         JB_PROPAGATE(conv_gemm_tc2(all, s));
       } else {
         for (int q = 0; q < sc; ++q) {
