@@ -177,6 +177,9 @@ typedef struct {
   float* d_out_f32; int32_t out_f32_ld;
   void* d_out_hi; void* d_out_lo; int32_t out_bf_ld;
   void* d_out_act; float out_act_slope; int32_t out_act_ld;
+  /* act == 5 (SnakeBeta, jatts/modules/matchatts/transformer.py:28-102, after its own Linear): x + sin(x * a[n])^2 * ib[n];
+   * n_pad floats each, a = exp(alpha), ib = 1 / (exp(beta) + 1e-9).  Split GEMMs with K <= 512 only. */
+  const float* d_snake_a; const float* d_snake_ib;
 } jatts_conv_gemm_args;
 /* impl 0 = tcgen05 kernel (the product kernel), 1 = CUDA-core twin (test-only cross-check) */
 JATTS_API int jatts_op_conv_gemm(const jatts_conv_gemm_args* a, int32_t impl, void* stream);

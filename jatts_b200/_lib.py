@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JATTS_B200_LIB") or os.path.join(_HERE, "lib", "libjatts_b200.so")
 
 JATTS_F32, JATTS_BF16, JATTS_I64, JATTS_I32, JATTS_F16 = 0, 1, 2, 3, 4
-ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_GLU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_GLU, ACT_SNAKE = 0, 1, 2, 3, 4, 5
 
 
 class Tensor(C.Structure):
@@ -56,6 +56,7 @@ class ConvGemmArgs(C.Structure):
         ("d_out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("d_out_hi", C.c_void_p), ("d_out_lo", C.c_void_p), ("out_bf_ld", C.c_int32),
         ("d_out_act", C.c_void_p), ("out_act_slope", C.c_float), ("out_act_ld", C.c_int32),
+        ("d_snake_a", C.c_void_p), ("d_snake_ib", C.c_void_p),
     ]
 
 

@@ -27,6 +27,7 @@ extern "C" int jatts_op_conv_gemm(const jatts_conv_gemm_args* a, int32_t impl, v
   e.out_f32 = a->d_out_f32; e.out_f32_ld = a->out_f32_ld;
   e.out_hi = static_cast<bf16*>(a->d_out_hi); e.out_lo = static_cast<bf16*>(a->d_out_lo); e.out_bf_ld = a->out_bf_ld;
   e.out_act = static_cast<bf16*>(a->d_out_act); e.out_act_slope = a->out_act_slope; e.out_act_ld = a->out_act_ld;
+  e.snake_a = a->d_snake_a; e.snake_ib = a->d_snake_ib;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return impl == 0 ? conv_gemm_tc(p, s) : conv_gemm_simt_debug(p, s);
 }

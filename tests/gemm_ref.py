@@ -62,6 +62,9 @@ class Case:
         if accum == "bf16":
             self.acc_t = self.acc_t.to(torch.bfloat16)
         self.sentinel = 768.0  # exactly representable in bf16 / fp16
+        # SnakeBeta constants per output column (transformer.py:28-102 with alpha_logscale: a = exp(alpha), ib = 1 / (exp(beta) + 1e-9))
+        self.snake_a = torch.exp(0.5 * torch.randn(self.n_pad, generator=g)) if act == _lib.ACT_SNAKE else None
+        self.snake_ib = 1.0 / (torch.exp(0.5 * torch.randn(self.n_pad, generator=g)) + 1e-9) if act == _lib.ACT_SNAKE else None
 
     # ---- fp64 reference --------------------------------------------------------------------------
     def reference(self):
@@ -123,6 +126,9 @@ class Case:
             return torch.where(x > 0, x, x * self.slope)
         if self.act == _lib.ACT_TANH:
             return torch.tanh(x)
+        if self.act == _lib.ACT_SNAKE:
+            n = x.shape[1]
+            return x + self.snake_ib[:n].double() * torch.sin(x * self.snake_a[:n].double()) ** 2
         return x
 
     # ---- device run --------------------------------------------------------------------------------
@@ -156,6 +162,10 @@ class Case:
         bias = self.bias.to(dev) if self.bias is not None else None
         args.d_bias = bias.data_ptr() if bias is not None else None
         args.act, args.slope, args.scale = self.act, self.slope, self.scale
+        sn_a = self.snake_a.to(dev) if self.snake_a is not None else None
+        sn_ib = self.snake_ib.to(dev) if self.snake_ib is not None else None
+        args.d_snake_a = sn_a.data_ptr() if sn_a is not None else None
+        args.d_snake_ib = sn_ib.data_ptr() if sn_ib is not None else None
         res = self.res_t.to(dev) if self.res_t is not None else None
         if self.res == "f32":
             args.d_res_f32 = res.data_ptr()
