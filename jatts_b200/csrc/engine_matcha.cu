@@ -226,12 +226,12 @@ static int estimator_step(jatts_matcha* h, const RowLayout& L, const RowLayout& 
   ++r;
   // ---- down 1 (half rate): resnet -> transformers -> skip 1 + Conv1d(k3)
   JB_PROPAGATE(resnet_block(h, h->res[r], h->p2_hi, h->p2_lo, C, Lh, temb + r * C, s));
-  JB_PROPAGATE(transformers(h, r, Lh, max_len / 2, h->p0_hi, h->p0_lo, C, s));
-  JB_PROPAGATE(copy_into_cat(h->p0_hi, h->p0_lo, C, Lh.n_rows, h->cat1_hi, h->cat1_lo, 1, s));
+  // skip 1 is written straight into the second half of cat1 (row pitch 2C) and the convolution reads it from there
+  JB_PROPAGATE(transformers(h, r, Lh, max_len / 2, h->cat1_hi + C, h->cat1_lo + C, 2 * C, s));
   {
     ConvGemmEpilogue e{};
     e.out_hi = h->p2_hi; e.out_lo = h->p2_lo; e.out_bf_ld = C;
-    JB_PROPAGATE(split_conv(h->down1, h->p0_hi, h->p0_lo, C, Lh, e, s));
+    JB_PROPAGATE(split_conv(h->down1, h->cat1_hi + C, h->cat1_lo + C, 2 * C, Lh, e, s));
   }
   ++r;
   // ---- mid blocks (half rate); the last one writes the first half of cat1

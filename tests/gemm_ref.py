@@ -63,8 +63,8 @@ class Case:
             self.acc_t = self.acc_t.to(torch.bfloat16)
         self.sentinel = 768.0  # exactly representable in bf16 / fp16
         # SnakeBeta constants per output column (transformer.py:28-102 with alpha_logscale: a = exp(alpha), ib = 1 / (exp(beta) + 1e-9))
-        self.snake_a = torch.exp(0.5 * torch.randn(self.n_pad, generator=g)) if act == _lib.ACT_SNAKE else None
-        self.snake_ib = 1.0 / (torch.exp(0.5 * torch.randn(self.n_pad, generator=g)) + 1e-9) if act == _lib.ACT_SNAKE else None
+        self.snake_a = torch.exp(0.3 * torch.randn(self.n_pad, generator=g)) if act == _lib.ACT_SNAKE else None
+        self.snake_ib = 1.0 / (torch.exp(0.3 * torch.randn(self.n_pad, generator=g)) + 1e-9) if act == _lib.ACT_SNAKE else None
 
     # ---- fp64 reference --------------------------------------------------------------------------
     def reference(self):

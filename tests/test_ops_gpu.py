@@ -29,8 +29,9 @@ CASES = {
     "split_gemm":      (dict(m=333, c_in=384, n=384, split_mode=True, res="f32", scale=0.5), 2e-5),
     "split_conv_k3":   (dict(m=450, c_in=384, n=1536, taps=3, split_mode=True, act=A.ACT_RELU, out=("f32", "hi", "lo")), 2e-5),
     "split_n80":       (dict(m=300, c_in=384, n=80, split_mode=True, out=("f32", "hi", "lo")), 2e-5),
-    # SnakeBeta in the single-chain epilogue (Matcha feed-forward, K = 512 -> N = 2048); sin.approx: |err| <= 2^-21 + |arg| 2^-24
-    "split_snake":     (dict(m=700, c_in=512, n=2048, split_mode=True, act=A.ACT_SNAKE, amp=2.0, out=("hi", "lo")), 3e-5),
+    # SnakeBeta in the single-chain epilogue (Matcha feed-forward, K = 512 -> N = 2048).  d/dx [x + ib sin^2(a x)] reaches
+    # 1 + a * ib ~ 3-4 with these constants: the budget is the plain split GEMM's 2e-5 times that amplification
+    "split_snake":     (dict(m=700, c_in=512, n=2048, split_mode=True, act=A.ACT_SNAKE, out=("hi", "lo")), 6e-5),
     "split_tanh_k5":   (dict(m=300, c_in=80, n=256, taps=5, split_mode=True, act=A.ACT_TANH, a_ld=128, out=("hi", "lo")), 2e-5),
     "split_glu":       (dict(m=300, c_in=384, n=384, split_mode=True, act=A.ACT_GLU), 2e-5),
     "persistent_wrap": (dict(m=128 * 160, c_in=64, n=128, taps=3, block_n=128, out=("hi",)), 1e-4),
