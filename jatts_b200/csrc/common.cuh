@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -105,6 +106,12 @@ __device__ __forceinline__ void split_pair16_sat(float a, float b, uint32_t& hi,
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// programmatic dependent launch (every kernel of the library is launched with the attribute, launch_pdl / launch_tc):
+// launch_dependents lets the NEXT kernel of the stream be scheduled as soon as every CTA of this one has started, so its
+// launch latency and prologue run under this kernel's tail; wait() returns once the PREVIOUS kernel has completed and its
+// writes are visible -- nothing a kernel reads or writes may be touched before it.  No-ops without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -120,5 +127,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 #endif
+
+// launch with programmatic stream serialization allowed (JATTS_B200_PDL=0 switches it off for A/B runs)
+template <typename Kern, typename... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem_bytes, cudaStream_t stream, Args... args) {
+  static const int pdl = getenv("JATTS_B200_PDL") ? atoi(getenv("JATTS_B200_PDL")) : 1;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = smem_bytes;
+  lc.stream = stream;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = la;
+  lc.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, kern, args...);
+}
 
 }  // namespace jb

@@ -12,6 +12,8 @@ namespace jb {
 // ------------------------------------------------------------------------------------------------
 __global__ void fill_layout_kernel(const int* __restrict__ seg_start, const int* __restrict__ seg_len, int nseg,
                                    int n_rows, uint8_t* __restrict__ mask, int* __restrict__ seg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   int lo = 0, hi = nseg - 1, b = -1;
@@ -26,7 +28,7 @@ __global__ void fill_layout_kernel(const int* __restrict__ seg_start, const int*
 int fill_layout(const int* seg_start, const int* seg_len, int nseg, int n_rows, uint8_t* frame_mask, int* frame_seg,
                 cudaStream_t s) {
   if (n_rows == 0) return 0;
-  fill_layout_kernel<<<ceil_div(n_rows, 256), 256, 0, s>>>(seg_start, seg_len, nseg, n_rows, frame_mask, frame_seg);
+  JB_CUDA_OK(launch_pdl(fill_layout_kernel, dim3(ceil_div(n_rows, 256)), dim3(256), 0, s, seg_start, seg_len, nseg, n_rows, frame_mask, frame_seg));
   JB_KERNEL_OK();
   return 0;
 }
@@ -38,6 +40,8 @@ struct GapBufs {
   int row_vec[16];
 };
 __global__ void zero_gap_rows_multi_kernel(GapBufs B, const int* __restrict__ seg_start, const int* __restrict__ seg_len) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y, k = blockIdx.z;
   const long long r = static_cast<long long>(seg_start[b]) + seg_len[b] + blockIdx.x;
   const int rv = B.row_vec[k];
@@ -53,7 +57,7 @@ int zero_gap_rows_multi(void* const* bufs, const int* row_bytes, int n, RowLayou
     B.p[i] = static_cast<uint4*>(bufs[i]);
     B.row_vec[i] = row_bytes[i] / 16;
   }
-  zero_gap_rows_multi_kernel<<<dim3(kGapRows, L.nseg, n), 64, 0, s>>>(B, L.seg_start, L.seg_len);
+  JB_CUDA_OK(launch_pdl(zero_gap_rows_multi_kernel, dim3(dim3(kGapRows, L.nseg, n)), dim3(64), 0, s, B, L.seg_start, L.seg_len));
   JB_KERNEL_OK();
   return 0;
 }
@@ -63,6 +67,8 @@ int zero_gap_rows_multi(void* const* bufs, const int* row_bytes, int n, RowLayou
 __global__ void embed_tokens_kernel(const long long* __restrict__ tokens, const int* __restrict__ tok_off,
                                     const float* __restrict__ emb, int vocab, int d, float scale, RowLayout L,
                                     float* __restrict__ x) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   const int b = L.frame_seg[r];
   if (b < 0) return;
@@ -79,7 +85,7 @@ int embed_tokens(const long long* tokens, const int* tok_off, const float* emb, 
                  RowLayout L, float* x, cudaStream_t s) {
   JB_REQUIRE(d % 4 == 0, -2, "embed: d % 4");
   if (L.n_rows == 0) return 0;
-  embed_tokens_kernel<<<L.n_rows, 96, 0, s>>>(tokens, tok_off, emb, vocab, d, scale, L, x);
+  JB_CUDA_OK(launch_pdl(embed_tokens_kernel, dim3(L.n_rows), dim3(96), 0, s, tokens, tok_off, emb, vocab, d, scale, L, x));
   JB_KERNEL_OK();
   return 0;
 }
@@ -94,6 +100,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int c, const float
                                  const float* __restrict__ beta, float eps, RowLayout L, float* __restrict__ y,
                                  bf16* __restrict__ hi, bf16* __restrict__ lo, int bf_ld,
                                  const float* __restrict__ w, float wb, float* __restrict__ dot_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= L.n_rows || !L.frame_mask[warp]) return;
@@ -163,8 +171,8 @@ int layernorm_rows(const float* x, int c, const float* gamma, const float* beta,
   JB_REQUIRE(c % 4 == 0 && c <= 128 * LN_MAXV, -2, "layernorm: C must be a multiple of 4 and <= 512");
   JB_REQUIRE(bf_ld % 4 == 0, -2, "layernorm: bf_ld % 4");
   if (L.n_rows == 0) return 0;
-  layernorm_kernel<false><<<ceil_div(L.n_rows, 8), 256, 0, s>>>(x, c, gamma, beta, eps, L, y, hi, lo, bf_ld, nullptr,
-                                                                0.f, nullptr);
+  JB_CUDA_OK(launch_pdl(layernorm_kernel<false>, dim3(ceil_div(L.n_rows, 8)), dim3(256), 0, s, x, c, gamma, beta, eps, L, y, hi, lo, bf_ld, nullptr,
+                                                                0.f, nullptr));
   JB_KERNEL_OK();
   return 0;
 }
@@ -173,14 +181,16 @@ int ln_dot_rows(const float* x, int c, const float* gamma, const float* beta, fl
   ProfileScope prof(s, PROF_LAYERNORM);
   JB_REQUIRE(c % 4 == 0 && c <= 128 * LN_MAXV, -2, "ln_dot: C must be a multiple of 4 and <= 512");
   if (L.n_rows == 0) return 0;
-  layernorm_kernel<true><<<ceil_div(L.n_rows, 8), 256, 0, s>>>(x, c, gamma, beta, eps, L, nullptr, nullptr, nullptr, 4,
-                                                               w, b, out);
+  JB_CUDA_OK(launch_pdl(layernorm_kernel<true>, dim3(ceil_div(L.n_rows, 8)), dim3(256), 0, s, x, c, gamma, beta, eps, L, nullptr, nullptr, nullptr, 4,
+                                                               w, b, out));
   JB_KERNEL_OK();
   return 0;
 }
 
 __global__ void split_rows_kernel(const float* __restrict__ x, int c, RowLayout L, bf16* __restrict__ hi,
                                   bf16* __restrict__ lo, int bf_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   if (!L.frame_mask[r]) return;
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
@@ -192,7 +202,7 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int c, RowLayout 
 }
 int split_rows(const float* x, int c, RowLayout L, bf16* hi, bf16* lo, int bf_ld, cudaStream_t s) {
   if (L.n_rows == 0) return 0;
-  split_rows_kernel<<<L.n_rows, 128, 0, s>>>(x, c, L, hi, lo, bf_ld);
+  JB_CUDA_OK(launch_pdl(split_rows_kernel, dim3(L.n_rows), dim3(128), 0, s, x, c, L, hi, lo, bf_ld));
   JB_KERNEL_OK();
   return 0;
 }
@@ -209,6 +219,8 @@ template <int K, int M>
 __global__ void __launch_bounds__(256)
 dwconv_swish_strip_kernel(const float* __restrict__ g, int c, const float* __restrict__ wT, const float* __restrict__ bias,
                           RowLayout L, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int PAD = (K - 1) / 2, TR = K * M, ROWS = TR + K - 1;
   extern __shared__ __align__(16) float dw_tile[];   // [ROWS][cb]: this CTA's block of channels
   const int b = blockIdx.y;
@@ -271,6 +283,8 @@ dwconv_swish_strip_kernel(const float* __restrict__ g, int c, const float* __res
 __global__ void dwconv_swish_kernel(const float* __restrict__ g, int c, const float* __restrict__ wT,
                                     const float* __restrict__ bias, int k, RowLayout L, bf16* __restrict__ out_hi,
                                     bf16* __restrict__ out_lo, int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   const int b = L.frame_seg[r];
   if (b < 0) return;
@@ -320,18 +334,18 @@ int dwconv_swish(const float* g, int c, const float* wT, const float* bias, int 
       const int smem = (31 * M + 30) * cb * 4;
       JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(dwconv_swish_strip_kernel<31, M>), smem));
       dim3 grid(ceil_div(max_len, 31 * M), L.nseg, c / cb);
-      dwconv_swish_strip_kernel<31, M><<<grid, cb, smem, s>>>(g, c, wT, bias, L, out_hi, out_lo, out_ld);
+      JB_CUDA_OK(launch_pdl(dwconv_swish_strip_kernel<31, M>, dim3(grid), dim3(cb), smem, s, g, c, wT, bias, L, out_hi, out_lo, out_ld));
     } else {
       constexpr int M = 9;
       const int smem = (7 * M + 6) * cb * 4;
       JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(dwconv_swish_strip_kernel<7, M>), smem));
       dim3 grid(ceil_div(max_len, 7 * M), L.nseg, c / cb);
-      dwconv_swish_strip_kernel<7, M><<<grid, cb, smem, s>>>(g, c, wT, bias, L, out_hi, out_lo, out_ld);
+      JB_CUDA_OK(launch_pdl(dwconv_swish_strip_kernel<7, M>, dim3(grid), dim3(cb), smem, s, g, c, wT, bias, L, out_hi, out_lo, out_ld));
     }
     JB_KERNEL_OK();
     return 0;
   }
-  dwconv_swish_kernel<<<L.n_rows, 96, 0, s>>>(g, c, wT, bias, k, L, out_hi, out_lo, out_ld);
+  JB_CUDA_OK(launch_pdl(dwconv_swish_kernel, dim3(L.n_rows), dim3(96), 0, s, g, c, wT, bias, k, L, out_hi, out_lo, out_ld));
   JB_KERNEL_OK();
   return 0;
 }
@@ -341,6 +355,8 @@ int dwconv_swish(const float* g, int c, const float* wT, const float* bias, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void add_speaker_kernel(const float* __restrict__ spembs, int spk_dim, const float* __restrict__ w,
                                    const float* __restrict__ bvec, int d, RowLayout L, float* __restrict__ hs) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sh[];  // [spk_dim] normalised embedding, then [d] projected
   float* e = sh;
   float* proj = sh + spk_dim;
@@ -371,7 +387,7 @@ __global__ void add_speaker_kernel(const float* __restrict__ spembs, int spk_dim
 int add_speaker(const float* spembs, int spk_dim, const float* w, const float* b, int d, RowLayout L, float* hs,
                 cudaStream_t s) {
   if (L.nseg == 0) return 0;
-  add_speaker_kernel<<<L.nseg, 256, sizeof(float) * (spk_dim + d), s>>>(spembs, spk_dim, w, b, d, L, hs);
+  JB_CUDA_OK(launch_pdl(add_speaker_kernel, dim3(L.nseg), dim3(256), sizeof(float) * (spk_dim + d), s, spembs, spk_dim, w, b, d, L, hs));
   JB_KERNEL_OK();
   return 0;
 }
@@ -390,6 +406,8 @@ __device__ __forceinline__ int regulator_frames(float dv, float alpha) {
 __global__ void durations_kernel(const float* __restrict__ logd, float alpha, RowLayout L,
                                  const int* __restrict__ tok_off, long long* __restrict__ dur_out,
                                  int* __restrict__ cum, int* __restrict__ n_frames) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int lane = threadIdx.x;
   const int s0 = L.seg_start[b], T = L.seg_len[b];
@@ -436,13 +454,15 @@ __global__ void durations_kernel(const float* __restrict__ logd, float alpha, Ro
 int durations_and_scan(const float* logd, float alpha, RowLayout L, const int* tok_off, long long* dur_out, int* cum,
                        int* n_frames, cudaStream_t s) {
   if (L.nseg == 0) return 0;
-  durations_kernel<<<L.nseg, 32, 0, s>>>(logd, alpha, L, tok_off, dur_out, cum, n_frames);
+  JB_CUDA_OK(launch_pdl(durations_kernel, dim3(L.nseg), dim3(32), 0, s, logd, alpha, L, tok_off, dur_out, cum, n_frames));
   JB_KERNEL_OK();
   return 0;
 }
 
 __global__ void gather_scalar_kernel(const float* __restrict__ in, RowLayout L, const int* __restrict__ tok_off,
                                      float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= L.n_rows) return;
   const int b = L.frame_seg[r];
@@ -451,7 +471,7 @@ __global__ void gather_scalar_kernel(const float* __restrict__ in, RowLayout L, 
 }
 int gather_scalar(const float* in, RowLayout L, const int* tok_off, float* out, cudaStream_t s) {
   if (L.n_rows == 0) return 0;
-  gather_scalar_kernel<<<ceil_div(L.n_rows, 256), 256, 0, s>>>(in, L, tok_off, out);
+  JB_CUDA_OK(launch_pdl(gather_scalar_kernel, dim3(ceil_div(L.n_rows, 256)), dim3(256), 0, s, in, L, tok_off, out));
   JB_KERNEL_OK();
   return 0;
 }
@@ -465,6 +485,8 @@ __global__ void length_regulate_kernel(const float* __restrict__ hs, const float
                                        const float* __restrict__ be, int d, float scale, RowLayout Lt,
                                        const int* __restrict__ cum, RowLayout Lf, const int* __restrict__ frame_off,
                                        float* __restrict__ x_out, int* __restrict__ lr_index) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= Lf.n_rows) return;
@@ -501,8 +523,8 @@ int length_regulate(const float* hs, const float* pitch, const float* energy, co
   ProfileScope prof(s, PROF_LENGTH_REGULATE);
   JB_REQUIRE(d % 4 == 0, -2, "length_regulate: d % 4");
   if (Lframe.n_rows == 0) return 0;
-  length_regulate_kernel<<<ceil_div(Lframe.n_rows, 8), 256, 0, s>>>(hs, pitch, energy, wp, bp, we, be, d, scale, Ltext,
-                                                                    cum, Lframe, frame_off, x_out, lr_index);
+  JB_CUDA_OK(launch_pdl(length_regulate_kernel, dim3(ceil_div(Lframe.n_rows, 8)), dim3(256), 0, s, hs, pitch, energy, wp, bp, we, be, d, scale, Ltext,
+                                                                    cum, Lframe, frame_off, x_out, lr_index));
   JB_KERNEL_OK();
   return 0;
 }
@@ -512,6 +534,8 @@ int length_regulate(const float* hs, const float* pitch, const float* energy, co
 // ------------------------------------------------------------------------------------------------
 __global__ void unpack_rows_kernel(const float* __restrict__ in, int in_ld, int c, RowLayout L,
                                    const int* __restrict__ off, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   const int b = L.frame_seg[r];
   if (b < 0) return;
@@ -520,13 +544,15 @@ __global__ void unpack_rows_kernel(const float* __restrict__ in, int in_ld, int 
 }
 int unpack_rows(const float* in, int in_ld, int c, RowLayout L, const int* off, float* out, cudaStream_t s) {
   if (L.n_rows == 0) return 0;
-  unpack_rows_kernel<<<L.n_rows, 96, 0, s>>>(in, in_ld, c, L, off, out);
+  JB_CUDA_OK(launch_pdl(unpack_rows_kernel, dim3(L.n_rows), dim3(96), 0, s, in, in_ld, c, L, off, out));
   JB_KERNEL_OK();
   return 0;
 }
 __global__ void pack_mel_affine_kernel(const float* __restrict__ mel, int c, const float* __restrict__ a,
                                        const float* __restrict__ bb, RowLayout L, const int* __restrict__ off,
                                        bf16* __restrict__ out, int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   const int b = L.frame_seg[r];
   if (b < 0) {  // gap row: the operand buffer must read as zero padding here
@@ -541,7 +567,7 @@ __global__ void pack_mel_affine_kernel(const float* __restrict__ mel, int c, con
 int pack_mel_affine(const float* mel, int c, const float* a, const float* b, RowLayout L, const int* off, bf16* out,
                     int out_ld, cudaStream_t s) {
   if (L.n_rows == 0) return 0;
-  pack_mel_affine_kernel<<<L.n_rows, 96, 0, s>>>(mel, c, a, b, L, off, out, out_ld);
+  JB_CUDA_OK(launch_pdl(pack_mel_affine_kernel, dim3(L.n_rows), dim3(96), 0, s, mel, c, a, b, L, off, out, out_ld));
   JB_KERNEL_OK();
   return 0;
 }
@@ -557,6 +583,8 @@ static constexpr int OC_MAXK = 7;
 __global__ void output_conv_tanh_kernel(const bf16* __restrict__ x, int ld, int c, const float* __restrict__ w,
                                         float bias, int k, RowLayout L, int rate, const int* __restrict__ frame_off,
                                         float* __restrict__ wave, short* __restrict__ pcm, long long total_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float ws[];  // [k][c]
   for (int i = threadIdx.x; i < k * c; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -617,6 +645,8 @@ __global__ void __launch_bounds__(OCT_THREADS)
 output_conv32_tiled_kernel(const bf16* __restrict__ x, const float* __restrict__ w, float bias, int k, RowLayout L, int rate,
                            const int* __restrict__ frame_off, float* __restrict__ wave, short* __restrict__ pcm,
                            long long total_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t oct_sm[];
   float* ws = reinterpret_cast<float*>(oct_sm);   // [k][32]
   uint8_t* xs = oct_sm + 1024;                     // [OCT_TILE + k - 1][80 B]
@@ -676,14 +706,14 @@ int output_conv_tanh(const bf16* x, int ld, int c, const float* w, float bias, i
     const int smem = 1024 + (OCT_TILE + k - 1) * OCT_PITCH;
     JB_PROPAGATE(ensure_dynamic_smem(reinterpret_cast<const void*>(output_conv32_tiled_kernel),
                                      1024 + (OCT_TILE + OC_MAXK - 1) * OCT_PITCH));
-    output_conv32_tiled_kernel<<<static_cast<unsigned>((total + OCT_TILE - 1) / OCT_TILE), OCT_THREADS, smem, s>>>(
-        x, w, bias, k, L, rate, frame_off, wave, pcm, total);
+    JB_CUDA_OK(launch_pdl(output_conv32_tiled_kernel, dim3(static_cast<unsigned>((total + OCT_TILE - 1) / OCT_TILE)), dim3(OCT_THREADS), smem, s, 
+        x, w, bias, k, L, rate, frame_off, wave, pcm, total));
     JB_KERNEL_OK();
     return 0;
   }
   const long long threads = (total + OC_PER - 1) / OC_PER;
-  output_conv_tanh_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, sizeof(float) * k * c, s>>>(
-      x, ld, c, w, bias, k, L, rate, frame_off, wave, pcm, total);
+  JB_CUDA_OK(launch_pdl(output_conv_tanh_kernel, dim3(static_cast<unsigned>((threads + 127) / 128)), dim3(128), sizeof(float) * k * c, s, 
+      x, ld, c, w, bias, k, L, rate, frame_off, wave, pcm, total));
   JB_KERNEL_OK();
   return 0;
 }

@@ -12,6 +12,8 @@ namespace jb {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const float* __restrict__ x, int c, int groups, RowLayout L, float eps, float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int g = blockIdx.x, b = blockIdx.y;
   const int cg = c / groups, cg4 = cg >> 2;
   const int T = L.seg_len[b];
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(256)
 groupnorm_mish_kernel(const float* __restrict__ x, int c, int groups, const float2* __restrict__ stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ add,
                       RowLayout L, float* __restrict__ y, bf16* __restrict__ hi, bf16* __restrict__ lo, int bf_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= L.n_rows) return;
@@ -109,9 +113,9 @@ int groupnorm_mish_rows(const float* x, int c, int groups, const float* gamma, c
   JB_REQUIRE(groups > 0 && c % groups == 0 && (c / groups) % 4 == 0, -2, "groupnorm: channels per group must be a multiple of 4");
   JB_REQUIRE((hi != nullptr) == (lo != nullptr) && (y != nullptr || hi != nullptr) && bf_ld % 4 == 0, -2, "groupnorm: outputs");
   if (L.n_rows == 0 || L.nseg == 0) return 0;
-  groupnorm_stats_kernel<<<dim3(groups, L.nseg), 256, 0, s>>>(x, c, groups, L, eps, stats);
+  JB_CUDA_OK(launch_pdl(groupnorm_stats_kernel, dim3(dim3(groups, L.nseg)), dim3(256), 0, s, x, c, groups, L, eps, stats));
   JB_KERNEL_OK();
-  groupnorm_mish_kernel<<<ceil_div(L.n_rows, 8), 256, 0, s>>>(x, c, groups, stats, gamma, beta, add, L, y, hi, lo, bf_ld);
+  JB_CUDA_OK(launch_pdl(groupnorm_mish_kernel, dim3(ceil_div(L.n_rows, 8)), dim3(256), 0, s, x, c, groups, stats, gamma, beta, add, L, y, hi, lo, bf_ld));
   JB_KERNEL_OK();
   return 0;
 }
@@ -122,6 +126,8 @@ int groupnorm_mish_rows(const float* x, int c, int groups, const float* gamma, c
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_rows_split_kernel(const float* __restrict__ in, int c, float scale, RowLayout L, const int* __restrict__ off,
                                        float* __restrict__ y, int y_ld, bf16* __restrict__ hi, bf16* __restrict__ lo, int bf_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   const int b = L.frame_seg[r];
   const long long irow = b >= 0 ? off[b] + (r - L.seg_start[b]) : 0;
@@ -137,7 +143,7 @@ __global__ void pack_rows_split_kernel(const float* __restrict__ in, int c, floa
 int pack_rows_split(const float* in, int c, float scale, RowLayout L, const int* off, float* y, int y_ld, bf16* hi, bf16* lo,
                     int bf_ld, cudaStream_t s) {
   if (L.n_rows == 0) return 0;
-  pack_rows_split_kernel<<<L.n_rows, 96, 0, s>>>(in, c, scale, L, off, y, y_ld, hi, lo, bf_ld);
+  JB_CUDA_OK(launch_pdl(pack_rows_split_kernel, dim3(L.n_rows), dim3(96), 0, s, in, c, scale, L, off, y, y_ld, hi, lo, bf_ld));
   JB_KERNEL_OK();
   return 0;
 }

@@ -280,8 +280,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // staging) runs while the previous kernel of the stream drains its last tiles; pdl_wait() returns once that
 // kernel has completed and its writes are visible.  A kernel launched without the attribute sees both as no-ops.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (pdl_launch_dependents / pdl_wait: common.cuh)
 
 // one launch path for the tensor-core kernels: optional cluster dimension, optional programmatic serialization
 template <typename Kern, typename... Args>
