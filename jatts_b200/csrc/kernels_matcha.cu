@@ -81,16 +81,28 @@ groupnorm_mish_kernel(const float* __restrict__ x, int c, int groups, const floa
   if (r >= L.n_rows) return;
   const int b = L.frame_seg[r];
   const int cg = c / groups;
-  for (int i = lane * 4; i < c; i += 128) {
+  constexpr int MAXV = 4;   // float4 per lane: C <= 512 (checked by the launcher)
+  float4 v[MAXV];
+  // the row's loads are issued before any arithmetic (the exponential and the division of Mish would otherwise sit
+  // between them and leave one 16-byte load in flight per lane)
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    const int i = lane * 4 + u * 128;
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b >= 0 && i < c) v[u] = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * c + i);
+  }
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    const int i = lane * 4 + u * 128;
+    if (i >= c) break;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (b >= 0) {
-      const float4 v = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * c + i);
       const float2 st = stats[b * groups + i / cg];   // cg % 4 == 0: the four channels share a group
       const float4 ga = *reinterpret_cast<const float4*>(gamma + i), be = *reinterpret_cast<const float4*>(beta + i);
-      o.x = mish_f((v.x - st.x) * st.y * ga.x + be.x);
-      o.y = mish_f((v.y - st.x) * st.y * ga.y + be.y);
-      o.z = mish_f((v.z - st.x) * st.y * ga.z + be.z);
-      o.w = mish_f((v.w - st.x) * st.y * ga.w + be.w);
+      o.x = mish_f((v[u].x - st.x) * st.y * ga.x + be.x);
+      o.y = mish_f((v[u].y - st.x) * st.y * ga.y + be.y);
+      o.z = mish_f((v[u].z - st.x) * st.y * ga.z + be.z);
+      o.w = mish_f((v[u].w - st.x) * st.y * ga.w + be.w);
       if (add != nullptr) {
         const float4 a = *reinterpret_cast<const float4*>(add + i);
         o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
@@ -110,7 +122,8 @@ groupnorm_mish_kernel(const float* __restrict__ x, int c, int groups, const floa
 int groupnorm_mish_rows(const float* x, int c, int groups, const float* gamma, const float* beta, float eps, const float* add,
                         RowLayout L, float2* stats, float* y, bf16* hi, bf16* lo, int bf_ld, cudaStream_t s) {
   ProfileScope prof(s, PROF_LAYERNORM);
-  JB_REQUIRE(groups > 0 && c % groups == 0 && (c / groups) % 4 == 0, -2, "groupnorm: channels per group must be a multiple of 4");
+  JB_REQUIRE(groups > 0 && c % groups == 0 && (c / groups) % 4 == 0 && c <= 512, -2,
+             "groupnorm: channels per group must be a multiple of 4, C <= 512");
   JB_REQUIRE((hi != nullptr) == (lo != nullptr) && (y != nullptr || hi != nullptr) && bf_ld % 4 == 0, -2, "groupnorm: outputs");
   if (L.n_rows == 0 || L.nseg == 0) return 0;
   JB_CUDA_OK(launch_pdl(groupnorm_stats_kernel, dim3(dim3(groups, L.nseg)), dim3(256), 0, s, x, c, groups, L, eps, stats));
