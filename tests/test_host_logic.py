@@ -143,3 +143,29 @@ def test_shard_utterances_partitions_and_balances():
     assert shard_utterances(lens, 3) == shard_utterances(lens, 3)  # deterministic
     with pytest.raises(ValueError):
         shard_utterances(lens, 0)
+
+
+def test_narrow_transposed_convolution_as_one_three_tap_convolution():
+    """_pack.py::pack_hifigan: for s * C_out <= 128 the whole ConvTranspose1d(2s, s, p) is ONE 3-tap convolution with
+    N = s * C_out whose output row i is frames i*s .. i*s + s - 1 (engine_hifigan.cu uses it for the last stage).
+    Evaluated with torch on the PACKED (bf16) weights against F.conv_transpose1d with the same bf16 weights: exact."""
+    import torch.nn.functional as F
+
+    for cfg, i in ((recipes.HIFIGAN_V1_HOP300, 3), (recipes.HIFIGAN_TINY, 1)):
+        sd = recipes.make_hifigan_state_dict(cfg, 0)
+        out = _pack.pack_hifigan(sd, cfg, torch.ones(cfg["in_channels"]), torch.zeros(cfg["in_channels"]))
+        s = cfg["upsample_scales"][i]
+        ci, co = cfg["channels"] >> i, cfg["channels"] >> (i + 1)
+        assert s * co <= 128 and f"ups{i}.t3.hi" in out and tuple(out[f"ups{i}.t3.hi"].shape) == (3, 128, ci)
+        assert all(f"ups{j}.t3.hi" not in out for j in range(len(cfg["upsample_scales"])) if cfg["upsample_scales"][j] * (cfg["channels"] >> (j + 1)) > 128)
+        w3 = out[f"ups{i}.t3.hi"].double()
+        wref = sd[f"upsamples.{i}.1.weight"].to(torch.bfloat16).double()
+        x = torch.randn(11, ci, generator=torch.Generator().manual_seed(i), dtype=torch.float64)
+        want = F.conv_transpose1d(x.t().unsqueeze(0), wref, sd[f"upsamples.{i}.1.bias"].double(), stride=s,
+                                  padding=s // 2 + s % 2, output_padding=s % 2)[0].t()
+        z = torch.zeros(1, ci, dtype=torch.float64)
+        xp = torch.cat([z, x, z], 0)
+        n = s * co
+        got = xp[:-2] @ w3[0, :n].t() + xp[1:-1] @ w3[1, :n].t() + xp[2:] @ w3[2, :n].t() + out[f"ups{i}.t3.b"][:n].double()
+        assert float(w3[:, n:].abs().max()) == 0.0 and float(out[f"ups{i}.t3.b"][n:].abs().max()) == 0.0
+        assert want.shape == (11 * s, co) and float((got.reshape(11 * s, co) - want).abs().max()) < 1e-12
