@@ -313,23 +313,24 @@ def decode_items(model, vocoder, items: Sequence[dict], outdir: str, sampling_ra
             try:
                 run_batch(batch)
             except NotImplementedError as e:
-                # an utterance of the batch expands to more frames than the model's max_len: the reference has no such
-                # limit (it extends its positional table), so do not lose the rest of the batch -- retry one by one
-                # and report the utterances that really do not fit (raise --max-len to decode them)
-                if "max_len" not in str(e) or len(batch) == 1:
-                    if "max_len" in str(e):
-                        skipped.append(items[batch[0]]["sample_id"])
-                        logging.warning("utterance %s needs more than max_len frames: skipped (%s)", skipped[-1], e)
-                        continue
+                # an utterance of the batch expands to more frames than the model's max_len (the reference has no such
+                # limit: it extends its positional table) or, Matcha-TTS, to fewer than the 2 frames its decoder needs (the
+                # reference's output is empty for it): do not lose the rest of the batch -- retry one by one and report
+                # the utterances that really do not fit
+                fits = lambda err: not any(k in str(err) for k in ("max_len", "fewer than 2 frames"))
+                if fits(e):
                     raise
-                for j in batch:
+                for j in (batch if len(batch) > 1 else []):
                     try:
                         run_batch([j])
                     except NotImplementedError as e1:
-                        if "max_len" not in str(e1):
+                        if fits(e1):
                             raise
                         skipped.append(items[j]["sample_id"])
-                        logging.warning("utterance %s needs more than max_len frames: skipped (%s)", skipped[-1], e1)
+                        logging.warning("utterance %s cannot be synthesised: skipped (%s)", skipped[-1], e1)
+                if len(batch) == 1:
+                    skipped.append(items[batch[0]]["sample_id"])
+                    logging.warning("utterance %s cannot be synthesised: skipped (%s)", skipped[-1], e)
     finally:
         writer.close()
     wall = time.time() - t0
@@ -418,7 +419,7 @@ def main(argv=None) -> int:
     logging.info("rank %d/%d decoded %d utterances in %d batches: %.1f s of audio in %.2f s (%.0f x real time, %.0f utterances/s)%s" % (
         args.rank, args.world_size, res["utterances"], res["batches"], res["audio_seconds"], res["wall_seconds"],
         res["audio_seconds_per_second"], res["utterances_per_second"],
-        f"; skipped (longer than --max-len): {res['skipped']}" if res["skipped"] else ""))
+        f"; skipped (too long for --max-len, or too short for the Matcha decoder): {res['skipped']}" if res["skipped"] else ""))
     with open(os.path.join(args.outdir, f"decode_stats.rank{args.rank}.json"), "w") as f:
         import json
 
