@@ -351,8 +351,10 @@ class MatchaTTS(torch.nn.Module):
         if min(lens) <= 0:
             raise ValueError("empty utterance")
         tok = torch.cat([t.reshape(-1) for t in texts]).to(device=dev, dtype=torch.long).contiguous()
-        if bool(((tok < 0) | (tok >= self.idim)).any()):
-            raise IndexError("token id out of range for the embedding table")
+        # out-of-range ids raise IndexError as nn.Embedding does -- but the flag is only READ after the plan call below has
+        # synchronised the stream anyway (the kernels clamp such ids, nothing is indexed out of the table): reading it here
+        # would be a second host<->device round trip per batch, with the GPU idle while the host catches up
+        bad_ids = ((tok < 0) | (tok >= self.idim)).any()
         if (self.spk_embed_dim is None) != (spembs is None):
             raise ValueError("spembs must be given iff the model was built with spk_embed_dim")
         sp_ptr = None
@@ -364,7 +366,10 @@ class MatchaTTS(torch.nn.Module):
             stream = torch.cuda.current_stream(dev).cuda_stream
             h_lens = (C.c_int32 * n)(*lens)
             h_frames = (C.c_int32 * n)()
-            _lib.check(_lib.lib.jatts_matcha_plan(handle, tok.data_ptr(), h_lens, n, sp_ptr, h_frames, stream), "matcha_plan")
+            rc = _lib.lib.jatts_matcha_plan(handle, tok.data_ptr(), h_lens, n, sp_ptr, h_frames, stream)
+            if bool(bad_ids):
+                raise IndexError("token id out of range for the embedding table")  # what nn.Embedding raises
+            _lib.check(rc, "matcha_plan")
             frames = list(h_frames)
             tot_f, tot_t = sum(frames), sum(lens)
             if callable(noise):
