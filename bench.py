@@ -537,6 +537,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     kept = []
     cpu_audio, cpu_times = time_cpu(4, reps=20, warm=1, seed0=0, keep=kept)   # ~10 s of CPU work
     cpu_value = cpu_audio * len(cpu_times) / sum(cpu_times)
+    # the recipe's own setting is ONE thread (egs/*/tts1/path.sh:15 exports OMP_NUM_THREADS=1): one utterance, 3 repetitions
+    torch.set_num_threads(1)
+    st_audio, st_times = time_cpu(1, reps=3, warm=1, seed0=0)
+    torch.set_num_threads(cpu_cores)
+    med = lambda v: sorted(v)[len(v) // 2]
     from oracle import hifigan as ohg
     parity = {"rows": 2, "durations_equal": True, "mel_max_abs": 0.0, "wave_ac_snr_db": 1e9}
     for i in range(2):   # rows 0 and 1 of the TIMED batch against the oracle
@@ -585,7 +590,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "host_cpus": cpu_cores,
                          "sample": "4 of the 64 utterances (50 phonemes each) x 20 repetitions after 1 warm-up, per-utterance loop as "
                                    "tts_decode.py; oracle port of the reference arithmetic, fp32 torch CPU, all host cores "
-                                   "(torch intra-op threads = os.cpu_count())"},
+                                   "(torch intra-op threads = os.cpu_count())",
+                         "best": cpu_audio / min(cpu_times), "median": cpu_audio / med(cpu_times),
+                         "single_thread": {"value": st_audio * len(st_times) / sum(st_times), "best": st_audio / min(st_times),
+                                           "median": st_audio / med(st_times), "cores": 1,
+                                           "sample": "1 utterance x 3 repetitions after 1 warm-up with torch.set_num_threads(1): the "
+                                                     "recipe's own OMP_NUM_THREADS=1 (egs/*/tts1/path.sh:15)"}},
     }
     print(json.dumps(line), flush=True)
 
