@@ -321,7 +321,6 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       constexpr uint32_t idesc1 = make_idesc(BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
       constexpr uint32_t idesc2 = make_idesc(2 * BLOCK_M2, BLOCK_N, /*is_bf16=*/true);
       constexpr uint32_t idesc = PAIR ? idesc2 : idesc1;
-      constexpr bool pair = PAIR;
       const int pipe = 0;
       Ring rs(0, STAGES), ra(0, C::A_STAGES), rb(0, B_DEPTH);
       const uint32_t w_addr = smem_u32(w_base);

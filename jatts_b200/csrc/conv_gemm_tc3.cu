@@ -393,7 +393,6 @@ gemm_split_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                 v[i] = a * (1.0f / (1.0f + __expf(-gt))) * P.scale;
               }
             } else {
-#pragma unroll
               float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
               if constexpr (ACTK == 3) {   // warp-uniform addresses: one broadcast transaction each, L1 resident
                 const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.sn_a + n0 + tc + 4 * q));
