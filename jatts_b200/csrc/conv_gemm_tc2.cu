@@ -57,6 +57,7 @@ struct KernelParams2 {
   int w_row0, w_tap_stride;       // weight rows of tap t: w_row0 + t*w_tap_stride (+ n0)
   int store_row_off;              // output row coordinate = m0 + store_row_off
   int mask_mul, mask_add, out_rows;  // validity: frame_mask[(row*mask_mul + mask_add) / rate], 0 <= . < out_rows
+  int n_slabs;                       // epilogue slabs per tile that hold real output columns (< N_SLABS for a partly filled N tile)
   int n_phases, phase_pp;            // > 0: N tile q is phase q of a polyphase transposed convolution (ConvGemmProblem::phases):
                                      // tap_off0, mask_add and the output tensor map depend on q
   long long* trace; // debug: per-role clock64 timeline of CTA 0 (jatts_debug_set_trace), else null
@@ -412,7 +413,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         Ring& re = (seq & 1) ? rg1 : rg0;
         const int m0 = ((grp / P.num_n_tiles) * cl + rank) * BLOCK_M2;
         const int n0 = (grp % P.num_n_tiles) * BLOCK_N;
-        for (int s = 0; s < C::N_SLABS; ++s) {
+        for (int s = 0; s < P.n_slabs; ++s) {
           const int e = re.idx;
           mbar_wait(&epempty_bar[e], re.phase ^ 1);
           re.next();
@@ -439,7 +440,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         Ring& re = (seq & 1) ? rg1 : rg0;
         const int m0 = ((grp / P.num_n_tiles) * cl + rank) * BLOCK_M2;
         const int n0 = (grp % P.num_n_tiles) * BLOCK_N;
-        for (int s = 0; s < C::N_SLABS; ++s) {
+        for (int s = 0; s < P.n_slabs; ++s) {
           const int e = re.idx;
           mbar_wait(&ready_bar[e], re.phase);  // the 128 threads of the tile's epilogue group wrote + fenced this slab
           re.next();
@@ -504,7 +505,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       if (warp == 4 && lane == 0) JB_TRACE(4, 0, seq);
       tc_fence_after();
 #pragma unroll 1
-      for (int s = 0; s < C::N_SLABS; ++s) {
+      for (int s = 0; s < P.n_slabs; ++s) {
         // each of the two warps of a TMEM lane group owns half of the slab's columns
         uint32_t r[CW];
         {
@@ -522,7 +523,7 @@ conv_bf16_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         re.next();
         if (s == 0 && warp == 4 && lane == 0) JB_TRACE(4, 1, seq);
         tmem_ld_wait();
-        if (s == C::N_SLABS - 1) {
+        if (s == P.n_slabs - 1) {
           // every TMEM read of this accumulator has completed: hand it back to the MMA warp right away
           tc_fence_before();
           __syncwarp();
@@ -693,6 +694,8 @@ static int launch2(const ConvGemmProblem& p, cudaStream_t stream) {
   kp.m_rows = p.m_rows;
   kp.num_m_tiles = ceil_div(p.m_rows, BLOCK_M2);
   kp.num_n_tiles = p.phases > 0 ? p.phases : (p.w_tap_stride != 0 ? p.n : p.n_pad) / BLOCK_N;
+  // a partly filled N tile (n < n_pad, one tile): the slabs beyond n hold no output column and are not processed at all
+  kp.n_slabs = (p.phases == 0 && p.n < p.n_pad) ? ceil_div(p.n, C::SLAB) : C::N_SLABS;
   kp.n_phases = p.phases;
   kp.phase_pp = p.phase_pp;
   kp.cl = cl;
