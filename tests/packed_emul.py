@@ -167,3 +167,91 @@ def emul_hifigan(p, cfg, mel):
     for j in range(k):
         y = y + xp[j:j + x.shape[0]] @ wo[j]
     return torch.tanh(y)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Matcha-TTS: the dataflow of jatts_b200/csrc/engine_matcha.cu from the table of _pack.py::pack_matcha
+# --------------------------------------------------------------------------------------------------------------
+def conv_off(p, name, x, n, tap_off0):
+    """convolution with explicit first tap offset (the paired-row views): out[r] = sum_j x[r + tap_off0 + j] W_j"""
+    k = x.shape[1]
+    w = W(p, name, n, k)
+    taps = w.shape[0]
+    lo, hi = max(0, -tap_off0), max(0, tap_off0 + taps - 1)
+    xp = F.pad(x, (0, 0, lo, hi))
+    out = torch.zeros(x.shape[0], n)
+    for j in range(taps):
+        s0 = lo + tap_off0 + j
+        out += xp[s0:s0 + x.shape[0]] @ w[j].t()
+    return out + p[name + ".b"][:n]
+
+
+def gn_mish(p, name, x, add=None):
+    y = F.mish(F.group_norm(x.t().unsqueeze(0), 8, p[name + ".g"], p[name + ".b"], 1e-5)[0].t())
+    return y if add is None else y + add
+
+
+def resnet(p, r, x, temb_r, c):
+    h = gn_mish(p, f"dec.res{r}.gn1", conv(p, f"dec.res{r}.c1", x, c), temb_r)
+    h = gn_mish(p, f"dec.res{r}.gn2", conv(p, f"dec.res{r}.c2", h, c))
+    return h + conv(p, f"dec.res{r}.res", x, c)
+
+
+def transformer(p, name, x, heads, inner):
+    c = x.shape[1]
+    h = F.layer_norm(x, (c,), p[name + ".ln1.g"], p[name + ".ln1.b"], 1e-5)
+    qkv = conv(p, name + ".qkv", h, 3 * inner)
+    dh = inner // heads
+    ctx = torch.zeros(x.shape[0], inner)
+    for hd in range(heads):
+        sl = slice(hd * dh, (hd + 1) * dh)
+        att = torch.softmax(qkv[:, sl] @ qkv[:, inner + hd * dh:inner + (hd + 1) * dh].t() / math.sqrt(dh), dim=-1)
+        ctx[:, sl] = att @ qkv[:, 2 * inner + hd * dh:2 * inner + (hd + 1) * dh]
+    x = x + conv(p, name + ".out", ctx, c)
+    h = F.layer_norm(x, (c,), p[name + ".ln3.g"], p[name + ".ln3.b"], 1e-5)
+    y = conv(p, name + ".ff1", h, 4 * c)
+    y = y + p[name + ".snake.ib"] * torch.sin(y * p[name + ".snake.a"]) ** 2
+    return x + conv(p, name + ".ff2", y, c)
+
+
+def emul_matcha(p, cfg, text, z, temb, dts):
+    """text (T_text,), z (T, odim) noise already scaled, temb [steps, blocks, C], dts [steps] -> dict(feat_gen, duration)"""
+    d, od, c = cfg["adim"], cfg["odim"], cfg["decoder_channels"][0]
+    heads, inner = cfg["decoder_num_heads"], cfg["decoder_num_heads"] * cfg["decoder_attention_head_dim"]
+    nb, nm = cfg["decoder_n_blocks"], cfg["decoder_num_mid_blocks"]
+    hs = conformer(p, "enc", p["emb"][text] * math.sqrt(d), cfg["elayers"], cfg["aheads"], cfg["eunits"])
+    logd = predictor(p, "dur", hs, cfg["duration_predictor_layers"], cfg["duration_predictor_chans"])
+    dur = torch.clamp(torch.round(logd.exp() - 1.0), min=0).long()
+    dl = dur if int(dur.sum()) > 0 else torch.ones_like(dur)
+    cum = torch.cumsum(dl, 0)
+    olen = int(cum[-1]) - int(cum[-1]) % 2
+    idx = torch.searchsorted(cum, torch.arange(olen), right=True)
+    mu = conv(p, "enc_proj", hs[idx], od)
+    x = z[:olen].clone()
+
+    def tr(r, h):
+        for j in range(nb):
+            h = transformer(p, f"dec.tr{r}_{j}", h, heads, inner)
+        return h
+
+    for step in range(temb.shape[0]):
+        te = temb[step]
+        r = 0
+        h0 = tr(r, resnet(p, r, torch.cat([x, mu], 1), te[r], c))                      # down 0 (skip 0)
+        pairs = h0.reshape(olen // 2, 2 * c)                                           # two frames per row
+        h = conv_off(p, "dec.down0", pairs, c, -1)                                     # stride-2 conv as a 2-tap conv
+        r += 1
+        h1 = tr(r, resnet(p, r, h, te[r], c))                                          # down 1 (skip 1)
+        h = conv(p, "dec.down1", h1, c)
+        r += 1
+        for _ in range(nm):
+            h = tr(r, resnet(p, r, h, te[r], c))
+            r += 1
+        h = tr(r, resnet(p, r, torch.cat([h, h1], 1), te[r], c))                       # up 0
+        h = conv(p, "dec.up0", h, 2 * c).reshape(olen, c)                              # ConvTranspose1d as a 3-tap conv
+        r += 1
+        h = tr(r, resnet(p, r, torch.cat([h, h0], 1), te[r], c))                       # up 1
+        h = conv(p, "dec.up1", h, c)
+        h = gn_mish(p, "dec.final.gn", conv(p, "dec.final", h, c))
+        x = x + dts[step] * conv(p, "dec.proj", h, od)
+    return dict(feat_gen=x, duration=dur)

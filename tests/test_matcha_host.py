@@ -109,3 +109,26 @@ def test_oracle_runs_on_the_recipe_weights():
     x = recipes.make_phonemes(6, 1, cfg["idim"])
     frames = int(om.matcha_inference(sd, cfg, x, recipes.make_noise(400, cfg["odim"], 0).t(), 2, 0.667)["feat_gen"].shape[0])
     assert frames > 0 and frames % 2 == 0
+
+
+def test_packed_dataflow_equals_the_oracle():
+    """the whole dataflow of engine_matcha.cu (paired-row down-sampling, 3-tap up-sampling, concatenation operands, stacked
+    q / k / v, SnakeBeta constants, time table, Euler update in the projection) evaluated on the CPU FROM THE PACKED TABLE
+    (tests/packed_emul.py::emul_matcha) against the oracle: a packing mistake shows up without a GPU"""
+    import packed_emul
+
+    cfg = recipes.SMALL_MATCHA
+    sd = recipes.make_matcha_state_dict(cfg, 7)
+    m = jatts_b200.MatchaTTS(**cfg)
+    m.load_state_dict(sd)
+    packed = _pack.pack_matcha(sd, m._cfg, 128)
+    steps, temp = 3, 0.667
+    temb, dts = m._time_table(steps, torch.device("cpu"))
+    for n_tok, seed in ((5, 1), (11, 2)):
+        x = recipes.make_phonemes(n_tok, 30 + seed, cfg["idim"])
+        z = recipes.make_noise(512, cfg["odim"], seed)
+        ref = om.matcha_inference(sd, cfg, x, z.t(), steps, temp)
+        em = packed_emul.emul_matcha(packed, cfg, x, z * temp, temb, list(dts))
+        assert torch.equal(ref["duration"], em["duration"])
+        assert em["feat_gen"].shape == ref["feat_gen"].shape
+        assert float((em["feat_gen"] - ref["feat_gen"]).abs().max()) < 2e-4
