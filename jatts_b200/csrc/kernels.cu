@@ -232,22 +232,20 @@ dwconv_swish_strip_kernel(const float* __restrict__ g, int c, const float* __res
   const long long base = L.seg_start[b];
   const int c4n = cb >> 2;
   const int n4 = ROWS * c4n;
-  for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {   // 4 independent 16-byte loads in flight per thread
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
-      const int rr = i / c4n, q = i - rr * c4n;
-      const int t = r0 - PAD + rr;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < n4 && t >= 0 && t < T) v[u] = reinterpret_cast<const float4*>(g + (base + t) * c + c0)[q];
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < n4) reinterpret_cast<float4*>(dw_tile)[i] = v[u];
-    }
+  // the whole tile is put in flight at once with cp.async (16 bytes per request, zero fill outside the utterance: src-size 0);
+  // with register-staged loads a CTA had 12 KB of its 70 KB tile in flight and spent most of its life waiting for it
+  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(dw_tile));
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int rr = i / c4n, q = i - rr * c4n;
+    const int t = r0 - PAD + rr;
+    const bool in = t >= 0 && t < T;
+    const float* src = in ? g + (base + t) * c + c0 + q * 4 : g;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + static_cast<uint32_t>(i) * 16u), "l"(src),
+                 "r"(in ? 16 : 0)
+                 : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const int ch = c0 + threadIdx.x;
   float w[K], win[K];
