@@ -6,7 +6,7 @@
  *   jatts/vocoder/vocoder.py:56-67        Vocoder.decode(c)  (-> parallel_wavegan HiFiGANGenerator.inference)
  *
  * as they are called from jatts/bin/tts_decode.py:230,249 and jatts/trainers/fastspeech2.py:183,205.
- * The reference is pure Python; the host side that mirrors its classes lives in jatts_b200/*.py and binds
+ * The reference is pure Python; the host side that mirrors its classes lives in the Python package jatts_b200 and binds
  * these symbols with ctypes (INTEGRATION.md shows the stub).
  *
  * Conventions
