@@ -636,8 +636,8 @@ __global__ void output_conv_tanh_kernel(const bf16* __restrict__ x, int ld, int 
 }
 // C = 32 fast path: a CTA stages OCT_TILE + k - 1 input rows in shared memory with coalesced 16-byte loads (the
 // per-thread version above reads 16 bytes per 256-byte stride: 4x the sectors), row pitch 80 B so that the 128-bit
-// reads of 8 consecutive rows hit 8 different bank groups.  Thread t computes rows t, t+256, t+512, t+768 of the
-// tile at once, so every weight vector (a broadcast shared-memory load) feeds 4 outputs.
+// reads of 8 consecutive rows hit 8 different bank groups.  Thread t computes rows t, t+256, ... of the tile at once
+// (OCT_TILE / 256 outputs per thread), so every weight vector (a broadcast shared-memory load) feeds several outputs.
 static constexpr int OCT_THREADS = 256, OCT_PITCH = 80;
 
 template <int OCT_TILE>
